@@ -1,0 +1,176 @@
+/*
+ * nmpc_b200.h — C ABI of the B200-native batched NMPC solver.
+ *
+ * This is the drop-in boundary for the one hot path of
+ * wljungbergh/mpc-trajectory-generator: the per-step NMPC solve that the
+ * reference delegates to an OpEn-generated solver process,
+ *
+ *     solution = mng.call(parameters)          src/mpc/mpc_generator.py:206
+ *
+ * where `mng` is `og.tcp.OptimizerTcpManager(...)` (src/path_generator.py:218-222)
+ * and the optimisation problem is the one `MpcModule.build()` defines
+ * (src/mpc/mpc_generator.py:66-193).  Everything behind `mng` (JSON over TCP,
+ * the generated Rust crate, PANOC + ALM, the CasADi cost/gradient code) is
+ * replaced by the functions below; everything in front of it (parameter
+ * assembly in src/path_generator.py:290-403, A* seeding, plotting) stays in the
+ * reference's Python.
+ *
+ * Conventions
+ *   - plain C types only, caller-owned buffers, no exceptions across the ABI;
+ *   - every function returns an int status (NMPC_OK == 0) and records a
+ *     message retrievable with nmpc_last_error();
+ *   - a handle is bound to one CUDA device and is NOT thread-safe (the
+ *     reference drives one request at a time through one TCP manager);
+ *   - all floating point is IEEE binary64, like the reference
+ *     (Python float -> JSON -> Rust f64 -> CasADi double).
+ *
+ * Layouts
+ *   u  (decision vector, src/mpc/mpc_generator.py:70,83)  : [v0,w0,v1,w1,...], 2*N_hor
+ *   p  (parameter vector z0, src/mpc/mpc_generator.py:71-79,93-104; assembled at
+ *       src/path_generator.py:378-379), length nmpc_param_len():
+ *        [0:3]   x, y, theta            initial state
+ *        [3:5]   v, omega               last applied input (vel_init, omega_init)
+ *        [5:8]   xref, yref, thetaref   horizon-end reference (x_finish)
+ *        [8:10]  (unused by the cost)
+ *        [10:20] q, qv, qtheta, rv, rw, qN, qthetaN, qCTE, acc_penalty, omega_acc_penalty
+ *        [20:20+N]                      vel_ref[t]
+ *        next 3*Nobs                    static circles (x, y, r), zero padded
+ *        next 5*Ndynobs*N               ellipses, obstacle-major then time: (x, y, rx, ry, angle)
+ *        last 3*N                       reference points (x, y, theta) per step
+ *   y  (ALM multipliers for F1 = [lin acc (N); ang acc (N)], src/mpc/mpc_generator.py:157-162): 2*N_hor
+ */
+#ifndef NMPC_B200_H
+#define NMPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMPC_ABI_VERSION 1
+#define NMPC_NZ 20          /* scalar header of the parameter vector (configs/default.yaml:35) */
+#define NMPC_LBFGS_MAX 10   /* opengen default lbfgs_memory */
+#define NMPC_MAX_HORIZON 96 /* three 32-lane passes */
+
+/* status codes returned by the API itself */
+enum {
+    NMPC_OK = 0,
+    NMPC_ERR_INVALID = 1,  /* bad argument / unsupported size            */
+    NMPC_ERR_CUDA = 2,     /* CUDA runtime error (message has the detail) */
+    NMPC_ERR_NOMEM = 3
+};
+
+/* per-problem solver exit status (the strings are OpEn's `exit_status`, which the
+ * reference compares against config.bad_exit_codes, src/path_generator.py:393,
+ * configs/default.yaml:49) */
+enum {
+    NMPC_CONVERGED = 0,              /* "Converged"                     */
+    NMPC_NOT_CONVERGED_ITERATIONS = 1, /* "NotConvergedIterations"      */
+    NMPC_NOT_CONVERGED_OUT_OF_TIME = 2, /* "NotConvergedOutOfTime" (only if a cycle budget is set) */
+    NMPC_NOT_FINITE = 3              /* solver error 2000 in the reference's TCP reply:
+                                        is_ok() == False (src/mpc/mpc_generator.py:215-221) */
+};
+
+/* Build-time constants of the reference's generated solver
+ * (configs/default.yaml:6 "Changing these will require a rebuild") plus the
+ * opengen 0.6.4 SolverConfiguration defaults the reference relies on
+ * (src/mpc/mpc_generator.py:184-186 sets only tolerance and max duration). */
+typedef struct nmpc_config {
+    int32_t N_hor;    /* horizon length N (configs/default.yaml:7)  */
+    int32_t Nobs;     /* static circle slots (configs/default.yaml:38) */
+    int32_t Ndynobs;  /* dynamic ellipse slots (configs/default.yaml:39) */
+    int32_t lbfgs_memory;         /* 10 */
+    int32_t max_inner_iterations; /* 500 */
+    int32_t max_outer_iterations; /* 10 */
+    int32_t reserved0, reserved1;
+    double ts;                    /* configs/default.yaml:18 */
+    double lin_vel_min, lin_vel_max, ang_vel_max; /* set U, src/mpc/mpc_generator.py:151-153 */
+    double lin_acc_min, lin_acc_max, ang_acc_max; /* set C, src/mpc/mpc_generator.py:164-168 */
+    double tolerance;                 /* 1e-4, src/mpc/mpc_generator.py:185 */
+    double initial_tolerance;         /* 1e-4 */
+    double delta_tolerance;           /* 1e-4 */
+    double inner_tolerance_update;    /* 0.1  */
+    double penalty_update_factor;     /* 5.0  */
+    double initial_penalty;           /* 1.0  */
+    double sufficient_decrease_coeff; /* 0.1  */
+} nmpc_config;
+
+/* per-problem diagnostics; mirrors the fields of OpEn's TCP reply */
+typedef struct nmpc_stats {
+    int32_t exit_status;        /* same value as the status array */
+    int32_t outer_iterations;   /* num_outer_iterations */
+    int32_t inner_iterations;   /* num_inner_iterations (summed over outer iterations) */
+    int32_t n_cost_evals;       /* psi evaluations without gradient */
+    int32_t n_grad_evals;       /* psi + grad psi evaluations       */
+    int32_t reserved;
+    double last_norm_fpr;       /* last_problem_norm_fpr */
+    double delta_y_norm_over_c; /* f1_infeasibility      */
+    double f2_norm;             /* f2_norm               */
+    double penalty;             /* final penalty c       */
+    double cost;                /* f(u) without penalty terms */
+} nmpc_stats;
+
+typedef struct nmpc_handle nmpc_handle;
+
+/* fill `cfg` with configs/default.yaml sizes/bounds and the opengen defaults */
+void nmpc_default_config(nmpc_config* cfg);
+
+/* length of the parameter vector for a config:
+ * nz + N + 3*Nobs + 5*Ndynobs*N + 3*N  (src/mpc/mpc_generator.py:71) */
+int32_t nmpc_param_len(const nmpc_config* cfg);
+
+/* Replaces MpcModule.build() + OptimizerTcpManager(...).start()
+ * (src/mpc/mpc_generator.py:66-193, src/path_generator.py:218-220):
+ * binds a solver instance for `cfg` to CUDA device `device`. */
+int nmpc_create(const nmpc_config* cfg, int device, nmpc_handle** out);
+
+/* Replaces mng.kill() (src/path_generator.py:408,417; src/mpc/mpc_generator.py:220). Idempotent on NULL. */
+int nmpc_destroy(nmpc_handle* h);
+
+/* Replaces mng.ping() (src/path_generator.py:222): 0 if the device answers. */
+int nmpc_ping(nmpc_handle* h);
+
+/* Replaces mng.call(parameters) for ONE problem with the server-side state the
+ * reference relies on (src/mpc/mpc_generator.py:206 passes only `p`): the decision
+ * vector and the multipliers persist inside the handle between calls (first call:
+ * zeros).  u_out: 2*N, stats_out nullable. */
+int nmpc_call(nmpc_handle* h, const double* p, double* u_out, int32_t* exit_status, nmpc_stats* stats_out);
+
+/* forget the persisted warm start of nmpc_call (a freshly started server) */
+int nmpc_reset_warm_start(nmpc_handle* h);
+
+/* Batched solve, HOST buffers (copies inside the call).
+ *   P  [B, np]  row-major parameters
+ *   U  [B, 2N]  in: initial guess, out: solution (the projected half step, always inside U)
+ *   Y  [B, 2N]  in: initial multipliers, out: multiplier state a server would keep; nullable (zeros)
+ *   status [B], stats [B] nullable */
+int nmpc_solve_batch(nmpc_handle* h, int32_t B, const double* P, double* U, double* Y,
+                     int32_t* status, nmpc_stats* stats);
+
+/* Batched solve, DEVICE buffers on the handle's device, asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = the handle's own stream). Same arrays
+ * as nmpc_solve_batch. */
+int nmpc_solve_batch_device(nmpc_handle* h, int32_t B, const double* dP, double* dU, double* dY,
+                            int32_t* dstatus, nmpc_stats* dstats, void* stream);
+
+/* Parity hook: evaluate the augmented cost for B (p, u, c, y) tuples on the device:
+ *   psi[B], grad[B,2N], F1[B,2N], F2[B,Nobs+Ndynobs]   (host buffers, any output nullable)
+ *   psi = f + c/2 * ( dist^2_C(F1 + y/max(c,1)) + |F2|^2 ) */
+int nmpc_eval_batch(nmpc_handle* h, int32_t B, const double* P, const double* U, const double* c,
+                    const double* Y, double* psi, double* grad, double* F1, double* F2);
+
+/* number of kernel launches issued through this handle since creation */
+int64_t nmpc_launch_count(nmpc_handle* h);
+
+/* cumulative device time (ms) of the last solve launched through the host-buffer entry points */
+double nmpc_last_kernel_ms(nmpc_handle* h);
+
+const char* nmpc_last_error(nmpc_handle* h);
+const char* nmpc_exit_status_name(int32_t exit_status);
+int32_t nmpc_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMPC_B200_H */

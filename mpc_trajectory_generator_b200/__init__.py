@@ -1,0 +1,5 @@
+"""B200-native batched NMPC solver behind the solver-call surface of
+wljungbergh/mpc-trajectory-generator (mng.call, src/mpc/mpc_generator.py:206)."""
+from .solver import NmpcConfig, NmpcSolver, NmpcError, EXIT_STATUS_NAMES, STATS_DTYPE, param_len  # noqa: F401
+
+__all__ = ["NmpcConfig", "NmpcSolver", "NmpcError", "EXIT_STATUS_NAMES", "STATS_DTYPE", "param_len"]
