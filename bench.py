@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — NMPC solves/sec (N=20, batched) on B200, next to the CPU restatement.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload config2|config3|synthetic] [--batch B]
+
+A "step" is one pass of the hot path (one batched solve launch) over one batch of
+synthetic NMPC instances.  Default workload = BASELINE.json configs[1]: B=4096 random
+start/goal pairs on map complexity=3, N=20, first-step problems, cold start.
+Multi-GPU (torchrun, one rank per GPU): the batch dimension shards with no data-path
+collective — every rank solves its own B problems (weak scaling); the only NCCL traffic is
+a broadcast of the static map / config table from rank 0.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in
+HBM); `e2e` goes through the public host-buffer API (NmpcSolver.solve_batch_into:
+pinned host buffers, H2D + D2H inside the timed region).  `--impl reference` times the
+CPU restatement of the reference's OpEn path (oracle/, all host threads) on a bounded
+sample of the same workload — OpEn itself cannot be installed here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "nmpc_solves_per_sec"
+UNIT = "solves/s"
+
+
+def algorithmic_bytes(N, Nobs, Nd):
+    """8*np + 8*2N (U0 in) + 8*2N (U out) + 48 (status/stats)."""
+    npar = 20 + N + 3 * Nobs + 5 * Nd * N + 3 * N
+    return 8 * npar + 2 * 8 * 2 * N + 48
+
+
+def eval_flops(N, Nobs, Nd):
+    """SURVEY.md §8d estimate of one psi forward evaluation (gradient ~3x)."""
+    return N * (24 + 9 * Nobs + 16 * Nd + 18 * (N - 1)) + 10 * N
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name, batch, seed, N=20):
+    """-> (P, U0, Y0, host_cfg, description)"""
+    from mpc_trajectory_generator_b200 import workloads
+    from mpc_trajectory_generator_b200.host import assembly
+    hc = assembly.HostConfig.default(N_hor=N)
+    if name == "config2":
+        P, _ = workloads.first_step_batch(hc, complexity=3, B=batch, seed=seed)
+        desc = f"configs[1]: batch={batch} random start/goal pairs, map complexity=3, N={N}, first step, cold start"
+        return P, None, None, hc, desc
+    if name == "synthetic":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import nmpc_problems
+        P = nmpc_problems.synth(N, hc.Nobs, hc.Ndynobs, batch, seed=seed, active=False)
+        return P, None, None, hc, f"synthetic piecewise-linear references, batch={batch}, N={N}"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the OpEn-equivalent restatement (oracle/) on the host cores."""
+    if rank != 0:
+        return
+    from oracle import oracle_c
+    oracle_c.build()
+    P, U0, Y0, hc, desc = make_workload(args.workload, args.batch, args.seed)
+    cfg = oracle_c.default_config(N_hor=hc.N_hor, Nobs=hc.Nobs, Ndynobs=hc.Ndynobs)
+    threads = oracle_c.max_threads()
+    sample = min(args.ref_sample, P.shape[0])
+    Ps = P[:sample]
+    for _ in range(args.warmup):
+        oracle_c.solve_batch(cfg, Ps[:min(32, sample)])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, st, _ = oracle_c.solve_batch(cfg, Ps)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "sample": f"first {sample} problems of the batch per step"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"first {sample} problems of the batch, {args.steps} passes, "
+                                       f"OpenMP over problems ({threads} threads); OpEn-equivalent C restatement, "
+                                       f"OpEn itself is not installable here"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--ref-sample", type=int, default=1024, help="problems per step for the CPU arm")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the solver has no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    import torch.distributed as dist
+    import mpc_trajectory_generator_b200 as pkg
+    from mpc_trajectory_generator_b200 import workloads
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # rank r generates its own shard (weak scaling: per-GPU batch fixed)
+    P, U0, Y0, hc, desc = make_workload(args.workload, args.batch, args.seed + rank)
+    B = P.shape[0]
+    N, Nobs, Nd = hc.N_hor, hc.Nobs, hc.Ndynobs
+    cfg = workloads.solver_config_for(hc)
+    if world > 1:
+        # the only collective on this path: the batch-invariant table (config scalars + cost weights)
+        # goes out from rank 0 over NCCL; every rank then checks its own copy against it.
+        table = torch.tensor([cfg.ts, cfg.lin_vel_min, cfg.lin_vel_max, cfg.ang_vel_max, cfg.lin_acc_min,
+                              cfg.lin_acc_max, cfg.ang_acc_max, cfg.tolerance] + [float(x) for x in P[0, 10:20]],
+                             dtype=torch.float64, device=dev)
+        mine = table.clone()
+        dist.broadcast(table, src=0)
+        assert torch.equal(table, mine), "static table differs across ranks"
+    solver = pkg.NmpcSolver(cfg, device=local_rank)
+    n2 = 2 * N
+
+    # ---------------- device-resident arm (`value`) ----------------
+    dP = torch.from_numpy(P).to(dev)
+    dU0 = torch.zeros((B, n2), dtype=torch.float64, device=dev) if U0 is None else torch.from_numpy(U0).to(dev)
+    dY0 = torch.zeros((B, n2), dtype=torch.float64, device=dev) if Y0 is None else torch.from_numpy(Y0).to(dev)
+    dU = torch.empty_like(dU0)
+    dY = torch.empty_like(dY0)
+    dstatus = torch.zeros(B, dtype=torch.int32, device=dev)
+    dstats = torch.zeros((B, 64), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+
+    def step_device():
+        dU.copy_(dU0)
+        dY.copy_(dY0)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        solver.solve_batch_device(B, dP.data_ptr(), dU.data_ptr(), dY.data_ptr(), dstatus.data_ptr(),
+                                  dstats.data_ptr(), stream.cuda_stream)
+        e1.record(stream)
+        return e0, e1
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+        flush.fill_(1)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = solver.launch_count
+    pairs = []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        pairs.append(step_device())
+        flush.fill_(1)          # L2 flush between timed iterations (outside the event pair)
+    sync_all()
+    t_wall = time.perf_counter() - t_wall0
+    launches = solver.launch_count - launches0
+    kernel_ms = [a.elapsed_time(b) for a, b in pairs]
+    total_ms = float(sum(kernel_ms))
+    clocks = sampler.stop() if rank == 0 else None
+    status = dstatus.cpu().numpy()
+    stats = np.frombuffer(dstats.cpu().numpy().tobytes(), dtype=pkg.STATS_DTYPE)
+
+    # ---------------- end-to-end arm (`e2e`): public API, pinned host buffers ----------------
+    hP = torch.from_numpy(P).pin_memory()
+    hU = torch.zeros((B, n2), dtype=torch.float64).pin_memory()
+    hY = torch.zeros((B, n2), dtype=torch.float64).pin_memory()
+    hstatus = torch.zeros(B, dtype=torch.int32).pin_memory()
+    U0h = np.zeros((B, n2)) if U0 is None else U0
+    Y0h = np.zeros((B, n2)) if Y0 is None else Y0
+
+    def step_e2e():
+        hU.numpy()[:] = U0h
+        hY.numpy()[:] = Y0h
+        t0 = time.perf_counter()
+        solver.solve_batch_into(hP.numpy(), hU.numpy(), hY.numpy(), hstatus.numpy(), None)
+        return time.perf_counter() - t0
+
+    for _ in range(2):
+        step_e2e()
+    sync_all()
+    e2e_s = 0.0
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        e2e_s += step_e2e()
+        flush.fill_(1)
+        torch.cuda.synchronize(dev)
+    h2d = P.nbytes + 2 * B * n2 * 8
+    d2h = 2 * B * n2 * 8 + B * 4
+
+    # ---------------- aggregate over ranks (max time) ----------------
+    t = torch.tensor([total_ms, e2e_s * 1e3 / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max, e2e_ms_step = float(t[0]), float(t[1])
+    value = world * B * args.steps / (total_ms_max * 1e-3)
+    e2e_value = world * B / (e2e_ms_step * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        abytes = algorithmic_bytes(N, Nobs, Nd)
+        ms_launch = total_ms / args.steps
+        achieved = abytes * B / (ms_launch * 1e-3) / 1e9
+        evals = float((stats["n_cost_evals"].astype(np.int64) + 3 * stats["n_grad_evals"].astype(np.int64)).sum())
+        gflops = evals * eval_flops(N, Nobs, Nd) / (ms_launch * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "batch_per_gpu": B, "N_hor": N, "Nobs": Nobs, "Ndynobs": Nd,
+                       "l2": "flushed between timed iterations (256 MiB write)", "seed": args.seed,
+                       "parity": "bit-exact vs oracle/ (tests/test_gpu_parity.py); OpEn itself not runnable here"},
+            "ms_per_solve": total_ms_max / args.steps / B,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms_step, "api": "NmpcSolver.solve_batch_into -> nmpc_solve_batch (C ABI), pinned host buffers"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+                         "algorithmic_bytes_per_solve": abytes,
+                         "note": "latency/FP64-ALU bound by construction (4128 B vs ~1e8 flop per solve); "
+                                 "see fp64 block and profiles/"},
+            "fp64": {"est_gflops": gflops, "peak_gflops_nominal": 148 * 64 * 2 * 1.965,
+                     "frac": gflops / (148 * 64 * 2 * 1.965),
+                     "evals_per_solve": float((stats["n_cost_evals"] + stats["n_grad_evals"]).mean()),
+                     "inner_iterations_mean": float(stats["inner_iterations"].mean())},
+            "exit_status_counts": np.bincount(status, minlength=4).tolist(),
+            "clocks": clocks,
+            "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            from oracle import oracle_c
+            oracle_c.build()
+            ocfg = oracle_c.default_config(N_hor=N, Nobs=Nobs, Ndynobs=Nd)
+            threads = oracle_c.max_threads()
+            t0 = time.perf_counter()
+            oracle_c.solve_batch(ocfg, P[:64], None if U0 is None else U0[:64], None if Y0 is None else Y0[:64])
+            rate = 64 / (time.perf_counter() - t0)
+            sample = int(min(B, max(64, rate * args.cpu_baseline_seconds)))
+            t0 = time.perf_counter()
+            Uo, Yo, sto, _ = oracle_c.solve_batch(ocfg, P[:sample], None if U0 is None else U0[:sample],
+                                                  None if Y0 is None else Y0[:sample])
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"first {sample} problems of rank 0's batch, one pass, OpenMP over "
+                                              f"problems; OpEn-equivalent C restatement (oracle/nmpc_oracle.c)",
+                                    "ms_per_solve_per_core": 1e3 * dt * threads / sample}
+            hU.numpy()[:] = U0h
+            hY.numpy()[:] = Y0h
+            solver.solve_batch_into(hP.numpy(), hU.numpy(), hY.numpy(), hstatus.numpy(), None)
+            line["parity_check"] = {"sample": sample, "flags_equal": bool(np.array_equal(hstatus.numpy()[:sample], sto)),
+                                    "bit_exact": bool(np.array_equal(hU.numpy()[:sample], Uo))}
+        print(json.dumps(line))
+    solver.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -116,6 +116,9 @@ __device__ __forceinline__ void nm_sincos(double x, double& s, double& c) {
     c = ((q + 1) & 2) ? -c0 : c0;
 }
 
+// Rectangle::project of OpEn is comparison-based: a NaN stays a NaN (and ends the solve as NotFinite)
+__device__ __forceinline__ double clampd(double x, double lo, double hi) { return (x < lo) ? lo : ((x > hi) ? hi : x); }
+
 // ---------------------------------------------------------------------------------
 // warp-ordered reductions
 __device__ __forceinline__ double butterfly(double a) {
@@ -629,8 +632,8 @@ struct Solver {
         for (int j = 0; j < P; j++) {
             gs[j].x = fma(-gamma, g[j].x, u[j].x);
             gs[j].y = fma(-gamma, g[j].y, u[j].y);
-            uh[j].x = act[j] ? fmin(fmax(gs[j].x, cfg.lin_vel_min), cfg.lin_vel_max) : 0.0;
-            uh[j].y = act[j] ? fmin(fmax(gs[j].y, -cfg.ang_vel_max), cfg.ang_vel_max) : 0.0;
+            uh[j].x = act[j] ? clampd(gs[j].x, cfg.lin_vel_min, cfg.lin_vel_max) : 0.0;
+            uh[j].y = act[j] ? clampd(gs[j].y, -cfg.ang_vel_max, cfg.ang_vel_max) : 0.0;
         }
         st(V_GSTEP, gs);
         st(V_UHALF, uh);
@@ -868,8 +871,8 @@ struct Solver {
             num_outer++;
 #pragma unroll
             for (int j = 0; j < P; j++) {
-                yl[j].x = fmin(fmax(yl[j].x, -Y_SET_BOUND), Y_SET_BOUND);
-                yl[j].y = fmin(fmax(yl[j].y, -Y_SET_BOUND), Y_SET_BOUND);
+                yl[j].x = clampd(yl[j].x, -Y_SET_BOUND, Y_SET_BOUND);
+                yl[j].y = clampd(yl[j].y, -Y_SET_BOUND, Y_SET_BOUND);
             }
             int iters = 0;
             const int inner = panoc_solve(u, iters);
@@ -901,8 +904,8 @@ struct Solver {
                 }
                 const double wa = (v - vp) * inv_ts, ww = (w - wp_) * inv_ts;
                 double za = wa + yl[j].x / pn.c, zw = ww + yl[j].y / pn.c;
-                za = fmin(fmax(za, cfg.lin_acc_min), cfg.lin_acc_max);
-                zw = fmin(fmax(zw, -cfg.ang_acc_max), cfg.ang_acc_max);
+                za = clampd(za, cfg.lin_acc_min, cfg.lin_acc_max);
+                zw = clampd(zw, -cfg.ang_acc_max, cfg.ang_acc_max);
                 yp[j].x = act[j] ? fma(pn.c, wa - za, yl[j].x) : 0.0;
                 yp[j].y = act[j] ? fma(pn.c, ww - zw, yl[j].y) : 0.0;
                 double d0 = yp[j].x - yl[j].x, d1 = yp[j].y - yl[j].y;

@@ -195,6 +195,20 @@ class NmpcSolver:
                     "nmpc_solve_batch")
         return U, Y, status, stats
 
+    def solve_batch_into(self, P, U, Y, status, stats=None):
+        """In-place variant for caller-owned (e.g. pinned) host buffers: U/Y are in/out
+        (initial guess / multipliers in, solution / multiplier state out); no copies here."""
+        B = P.shape[0]
+        for a, shape, dt in ((P, (B, self.np), np.float64), (U, (B, self.n2), np.float64),
+                             (Y, (B, self.n2), np.float64), (status, (B,), np.int32)):
+            if a.shape != shape or a.dtype != dt or not a.flags["C_CONTIGUOUS"]:
+                raise NmpcError(f"buffer must be C-contiguous {dt.__name__}{list(shape)}")
+        if stats is not None and (stats.dtype != STATS_DTYPE or stats.shape != (B,)):
+            raise NmpcError("stats must be STATS_DTYPE[B]")
+        self._check(self._lib.nmpc_solve_batch(self._h, B, _ptr(P), _ptr(U), _ptr(Y), status.ctypes.data_as(_ip),
+                                               None if stats is None else stats.ctypes.data_as(C.c_void_p)),
+                    "nmpc_solve_batch")
+
     # -- batch, device buffers (raw pointers, e.g. torch tensors' data_ptr()) ---------------
     def solve_batch_device(self, B, dP, dU, dY=0, dstatus=0, dstats=0, stream=0):
         self._check(self._lib.nmpc_solve_batch_device(self._h, int(B), dP, dU, dY or None, dstatus or None,

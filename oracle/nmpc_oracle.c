@@ -509,10 +509,12 @@ typedef struct {
     lbfgs_t lb;
 } panoc_t;
 
+/* Rectangle::project (constraints/rectangle.rs): comparison-based, so a NaN stays a NaN */
+static inline double clampd(double x, double lo, double hi) { return (x < lo) ? lo : ((x > hi) ? hi : x); }
 static void project_U(const staged* S, double* v) { /* Rectangle U, src/mpc/mpc_generator.py:151-153 */
     for (int t = 0; t < S->N; t++) {
-        v[2 * t] = fmin(fmax(v[2 * t], S->vmin), S->vmax);
-        v[2 * t + 1] = fmin(fmax(v[2 * t + 1], -S->wmax), S->wmax);
+        v[2 * t] = clampd(v[2 * t], S->vmin, S->vmax);
+        v[2 * t + 1] = clampd(v[2 * t + 1], -S->wmax, S->wmax);
     }
 }
 static void grad_step_half(panoc_t* C, const double* u) { /* gradient_step() + half_step() */
@@ -662,7 +664,7 @@ int nmpc_oracle_solve(const nmpc_config* cfg, const double* p, double* u, double
     double f2n = 0.0, f2np = 0.0, dyn = 0.0, dynp = 0.0;
     for (int outer = 0; outer < cfg->max_outer_iterations; outer++) {
         num_outer++;
-        for (int i = 0; i < n2; i++) y[i] = fmin(fmax(y[i], -Y_SET_BOUND), Y_SET_BOUND); /* project_on_set_y */
+        for (int i = 0; i < n2; i++) y[i] = clampd(y[i], -Y_SET_BOUND, Y_SET_BOUND); /* project_on_set_y */
         int iters = 0;
         int inner = panoc_solve(C, u, cfg->max_inner_iterations, &iters);
         inner_total += iters;
@@ -674,8 +676,8 @@ int nmpc_oracle_solve(const nmpc_config* cfg, const double* p, double* u, double
         double e[MAXT];
         for (int t = 0; t < N; t++) {
             double za = w[t] + y[t] / C->c, zw = w[N + t] + y[N + t] / C->c;
-            za = fmin(fmax(za, S.amin), S.amax);
-            zw = fmin(fmax(zw, -S.aamax), S.aamax);
+            za = clampd(za, S.amin, S.amax);
+            zw = clampd(zw, -S.aamax, S.aamax);
             yp[t] = fma(C->c, w[t] - za, y[t]);
             yp[N + t] = fma(C->c, w[N + t] - zw, y[N + t]);
             double d0 = yp[t] - y[t], d1 = yp[N + t] - y[N + t];

@@ -83,3 +83,125 @@ def test_warm_start_call_sequence(oracle, gpu_solver_factory):
         assert st == sto[0]
         assert np.array_equal(u, Uo[0])
         u_prev, y_prev = Uo, Yo
+
+
+def test_nan_input_flags_not_finite(oracle, gpu_solver_factory):
+    """a NaN in the parameters ends as NotFiniteComputation on both sides (reference: is_ok() False)."""
+    import mpc_trajectory_generator_b200 as pkg
+    g, o = _cfgs(pkg, oracle)
+    P = problems.synth(20, 10, 3, 4, seed=8, active=False)
+    P[1, 0] = np.nan
+    s = gpu_solver_factory(g)
+    U, Y, st, stats = s.solve_batch(P)
+    Uo, Yo, sto, _ = oracle.solve_batch(o, P)
+    assert st[1] == 3 and np.array_equal(st, sto)
+    ok = st != 3
+    assert np.array_equal(U[ok], Uo[ok])
+
+
+def test_empty_and_single(oracle, gpu_solver_factory):
+    import mpc_trajectory_generator_b200 as pkg
+    g, o = _cfgs(pkg, oracle)
+    s = gpu_solver_factory(g)
+    U, Y, st, stats = s.solve_batch(np.zeros((0, 430)))
+    assert U.shape == (0, 40) and st.shape == (0,)
+    P = problems.synth(20, 10, 3, 1, seed=2, active=False)
+    U, Y, st, stats = s.solve_batch(P)
+    Uo, _, sto, _ = oracle.solve_batch(o, P)
+    assert np.array_equal(U, Uo) and np.array_equal(st, sto)
+
+
+def test_golden_reference_run_replay(gpu_solver_factory):
+    """BASELINE config 1: the parameter sequence recorded from the UNMODIFIED reference
+    PathGenerator.run (tests/golden/config1_run.npz) replayed through nmpc_call, whose handle
+    keeps (u, y) between calls like OpEn's TCP server; every reply must equal the recorded one."""
+    import os
+    import mpc_trajectory_generator_b200 as pkg
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_run.npz"))
+    s = gpu_solver_factory(pkg.NmpcConfig.default())
+    s.reset_warm_start()
+    for k in range(g["P"].shape[0]):
+        u, st, stats, ms = s.call(g["P"][k])
+        assert st == g["status"][k] and stats["inner_iterations"] == g["inner"][k]
+        assert np.linalg.norm(u - g["U"][k]) <= REL_TOL * max(np.linalg.norm(g["U"][k]), 1e-12)
+        assert np.array_equal(u, g["U"][k])
+
+
+def test_manager_closed_loop_default_config():
+    """The OptimizerTcpManager-shaped object drives a full receding-horizon run (our host mirror of
+    src/path_generator.py:290-403) on map complexity=1 / configs/default.yaml and reaches the goal
+    exactly like the recorded reference run."""
+    import os
+    from mpc_trajectory_generator_b200.host import assembly, opengen_compat
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_run.npz"))
+    hc = assembly.HostConfig.default()
+    opengen_compat.configure(reference_config=hc)
+    mng = opengen_compat.OptimizerTcpManager("mpc_build/navigation")
+    mng.start()
+    mng.ping()
+    sc = assembly.Scenario(hc, assembly.load_maps()[1])
+    done, k = False, 0
+    while not done and k < 2500:
+        resp = mng.call(list(sc.parameters()))
+        assert resp.is_ok()
+        sol = resp.get()
+        assert sol.exit_status in ("Converged", "NotConvergedIterations") and sol.solve_time_ms > 0
+        done = sc.apply(sol.solution)
+        k += 1
+    mng.kill()
+    mng.kill()  # idempotent
+    assert done and k == g["P"].shape[0]
+    assert np.array_equal(np.array(sc.states[0::3]), g["xx"]) and np.array_equal(np.array(sc.states[1::3]), g["xy"])
+    bad = opengen_compat.OptimizerTcpManager()
+    bad.start()
+    r = bad.call([0.0] * 7)
+    assert not r.is_ok() and r.get().code == 3003
+    bad.kill()
+
+
+def test_full_size_properties(gpu_solver_factory):
+    """BASELINE.json full size (B=4096, N=20): size-independent properties — every reply lies in U,
+    flags are in the enum, the launch is deterministic, and a permutation of the batch permutes the
+    replies (no cross-problem coupling through the work queue or shared memory)."""
+    import mpc_trajectory_generator_b200 as pkg
+    g = pkg.NmpcConfig.default()
+    B = 4096
+    P = problems.synth(20, 10, 3, B, seed=123, active=False)
+    s = gpu_solver_factory(g)
+    U, Y, st, stats = s.solve_batch(P)
+    lo = np.tile([g.lin_vel_min, -g.ang_vel_max], 20)
+    hi = np.tile([g.lin_vel_max, g.ang_vel_max], 20)
+    assert np.all(U >= lo) and np.all(U <= hi)
+    assert set(np.unique(st)) <= {0, 1}
+    assert np.all(stats["exit_status"] == st)
+    conv = st == 0
+    assert conv.mean() > 0.3
+    assert np.all(stats["last_norm_fpr"][conv] < g.tolerance)
+    assert np.all(stats["f2_norm"][conv] <= g.delta_tolerance * 1.0000001)
+    U2, Y2, st2, _ = s.solve_batch(P)
+    assert np.array_equal(U, U2) and np.array_equal(st, st2)
+    perm = np.random.default_rng(0).permutation(B)
+    U3, Y3, st3, _ = s.solve_batch(P[perm])
+    assert np.array_equal(U3, U[perm]) and np.array_equal(st3, st[perm]) and np.array_equal(Y3, Y[perm])
+
+
+def test_device_pointer_entry(oracle, gpu_solver_factory):
+    """nmpc_solve_batch_device on torch tensors / torch's current stream (the path bench.py times)."""
+    import torch
+    import mpc_trajectory_generator_b200 as pkg
+    g, o = _cfgs(pkg, oracle)
+    B = 64
+    P = problems.synth(20, 10, 3, B, seed=31, active=False)
+    s = gpu_solver_factory(g)
+    dev = torch.device("cuda", 0)
+    dP = torch.from_numpy(P).to(dev)
+    dU = torch.zeros((B, 40), dtype=torch.float64, device=dev)
+    dY = torch.zeros((B, 40), dtype=torch.float64, device=dev)
+    dst = torch.zeros(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    n0 = s.launch_count
+    s.solve_batch_device(B, dP.data_ptr(), dU.data_ptr(), dY.data_ptr(), dst.data_ptr(), 0, stream.cuda_stream)
+    torch.cuda.synchronize(dev)
+    assert s.launch_count == n0 + 1
+    Uo, Yo, sto, _ = oracle.solve_batch(o, P)
+    assert np.array_equal(dU.cpu().numpy(), Uo) and np.array_equal(dst.cpu().numpy(), sto)
