@@ -208,7 +208,8 @@ def main():
     dstatus = torch.zeros(B, dtype=torch.int32, device=dev)
     dstats = torch.zeros((B, 64), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)   # the solve kernel, its input copies and the timing events share this stream
+    torch.cuda.set_stream(stream)
 
     def step_device():
         dU.copy_(dU0)

@@ -149,8 +149,8 @@ int nmpc_solve_batch(nmpc_handle* h, int32_t B, const double* P, double* U, doub
                      int32_t* status, nmpc_stats* stats);
 
 /* Batched solve, DEVICE buffers on the handle's device, asynchronous on `stream`
- * (a cudaStream_t passed as void*; NULL = the handle's own stream). Same arrays
- * as nmpc_solve_batch. */
+ * (a cudaStream_t passed as void*; NULL = CUDA's default stream, as for any cudaStream_t).
+ * Same arrays as nmpc_solve_batch; the caller orders its own copies on that stream. */
 int nmpc_solve_batch_device(nmpc_handle* h, int32_t B, const double* dP, double* dU, double* dY,
                             int32_t* dstatus, nmpc_stats* dstats, void* stream);
 

@@ -113,6 +113,15 @@ void nmpc_oracle_sincos(double x, double* s, double* c) {
     }
 }
 
+/* min/max written as compare-selects (the kernel uses the same forms): a NaN operand yields the
+ * constant, like C's fmax/fmin, and the sign of a zero result is fixed (+0). */
+static inline double sel_clamp01(double t) {
+    double r = (t > 0.0) ? t : 0.0;
+    return (r < 1.0) ? r : 1.0;
+}
+/* z - Proj_[lo,hi](z):  max(z - hi, 0) + min(z - lo, 0) */
+static inline double sel_excess(double z, double lo, double hi) { return (z > hi) ? z - hi : ((z < lo) ? z - lo : 0.0); }
+
 /* ------------------------------------------------------------------------- */
 /* warp-ordered reductions                                                     */
 
@@ -298,7 +307,7 @@ static double eval_psi(staged* S, const double* u, double c, const double* y, do
         for (int i = 1; i < N; i++) {
             double px = X[t] - S->s1x[i], py = Y[t] - S->s1y[i];
             double that = fma(px, S->sdx[i], py * S->sdy[i]) * S->sinv[i];
-            double tst = fmin(fmax(that, 0.0), 1.0);
+            double tst = sel_clamp01(that); /* fmin(fmax(t_hat, 0), 1), :138 */
             double ex = fma(tst, S->sdx[i], -px), ey = fma(tst, S->sdy[i], -py);
             double d2 = fma(ex, ex, ey * ey);
             if (d2 < best) { best = d2; bi = i; bex = ex; bey = ey; bth = that; }
@@ -375,8 +384,8 @@ static double eval_psi(staged* S, const double* u, double c, const double* y, do
         c0 = fma(S->ap, acc * acc, c0);
         c0 = fma(S->wp, aac * aac, c0);
         double za = fma(y ? y[t] : 0.0, inv_c, acc), zw = fma(y ? y[N + t] : 0.0, inv_c, aac);
-        double da = fmax(za - S->amax, 0.0) + fmin(za - S->amin, 0.0);
-        double dw = fmax(zw - S->aamax, 0.0) + fmin(zw + S->aamax, 0.0);
+        double da = sel_excess(za, S->amin, S->amax);   /* z - Proj_C(z) */
+        double dw = sel_excess(zw, -S->aamax, S->aamax);
         c0 = fma(hc, fma(da, da, dw * dw), c0);
         cl[t] = c0;
         Aa[t] = fma(c, da, (2.0 * S->ap) * acc) * inv_ts;
@@ -540,7 +549,10 @@ static void panoc_init(panoc_t* C, double* u) {
     /* cost and gradient at u; estimate_loc_lip perturbs u by h and LEAVES it perturbed */
     C->cost = eval_psi(S, u, C->c, C->y, C->grad, 0, 0);
     double hv[2 * MAXT], gh[2 * MAXT], e[MAXT];
-    for (int i = 0; i < n2; i++) hv[i] = fmax(DELTA_LIPSCHITZ, EPSILON_LIPSCHITZ * u[i]);
+    for (int i = 0; i < n2; i++) {
+        double e_ = EPSILON_LIPSCHITZ * u[i];
+        hv[i] = (e_ > DELTA_LIPSCHITZ) ? e_ : DELTA_LIPSCHITZ; /* max{delta, epsilon*u} */
+    }
     for (int t = 0; t < N; t++) e[t] = fma(hv[2 * t + 1], hv[2 * t + 1], hv[2 * t] * hv[2 * t]);
     double norm_h = sqrt(hsum(e, N, P));
     for (int i = 0; i < n2; i++) u[i] = u[i] + hv[i];
