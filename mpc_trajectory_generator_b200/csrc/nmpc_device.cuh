@@ -23,6 +23,12 @@
 #include "../../include/nmpc_b200.h"
 
 #define FULL 0xffffffffu
+#ifndef NMPC_OBS_QUICK
+#define NMPC_OBS_QUICK 0
+#endif
+#ifndef NMPC_CTE_STAGE
+#define NMPC_CTE_STAGE 0
+#endif
 #define MEMP1 (NMPC_LBFGS_MAX + 1)
 
 // OpEn PANOC constants (panoc_engine.rs) — see oracle/nmpc_oracle.c for the restatement notes
@@ -81,6 +87,7 @@ struct KArgs {
     // eval kernel only
     const double* cvec;
     double *psi, *grad, *F1, *F2;
+    long long* dbg;  // NMPC_PROFILE builds only: 8 cycle counters per problem
 };
 
 // ---------------------------------------------------------------------------------
@@ -467,7 +474,9 @@ struct Warp {
             constexpr int UNR = (P == 1) ? 4 : 2;
             uint32_t as = a_seg + 48u;
             int i = 1;
-            for (; i + UNR <= N; i += UNR, as += 48u * UNR) {  // UNR independent segments per trip (ILP)
+            // UNR segments per trip, written stage by stage: the SM issues in order, so independent
+            // chains only overlap if they are interleaved in the instruction stream
+            for (; i + UNR <= N; i += UNR, as += 48u * UNR) {
                 double2 s1[UNR], d[UNR];
                 double inv[UNR];
 #pragma unroll
@@ -478,6 +487,32 @@ struct Warp {
                 }
 #pragma unroll
                 for (int j = 0; j < P; j++) {
+#if NMPC_CTE_STAGE
+                    double px[UNR], py[UNR], tt[UNR], ex[UNR], ey[UNR], d2[UNR];
+#pragma unroll
+                    for (int q = 0; q < UNR; q++) {
+                        px[q] = X[j] - s1[q].x;
+                        py[q] = Y[j] - s1[q].y;
+                    }
+#pragma unroll
+                    for (int q = 0; q < UNR; q++) tt[q] = py[q] * d[q].y;
+#pragma unroll
+                    for (int q = 0; q < UNR; q++) tt[q] = fma(px[q], d[q].x, tt[q]);
+#pragma unroll
+                    for (int q = 0; q < UNR; q++) tt[q] = tt[q] * inv[q];
+#pragma unroll
+                    for (int q = 0; q < UNR; q++) tt[q] = sel_clamp01(tt[q]);
+#pragma unroll
+                    for (int q = 0; q < UNR; q++) {
+                        ex[q] = fma(tt[q], d[q].x, -px[q]);
+                        ey[q] = fma(tt[q], d[q].y, -py[q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < UNR; q++) d2[q] = ey[q] * ey[q];
+#pragma unroll
+                    for (int q = 0; q < UNR; q++) d2[q] = fma(ex[q], ex[q], d2[q]);
+#pragma unroll
+#else
                     double d2[UNR];
 #pragma unroll
                     for (int q = 0; q < UNR; q++) {
@@ -488,6 +523,7 @@ struct Warp {
                         d2[q] = fma(ex, ex, ey * ey);
                     }
 #pragma unroll
+#endif
                     for (int q = 0; q < UNR; q++) take_if_less(d2[q], i + q, best[j], bi[j]);
                 }
             }
@@ -525,7 +561,37 @@ struct Warp {
 
         // obstacle penalty F2: circles (non-padded ones), then this lane's time slice of each ellipse
         double pen = 0.0;
+#if NMPC_OBS_QUICK
+        bool hit = false;  // is any lane inside any obstacle?  (all tests issued back to back, one vote)
         {
+            uint32_t ac = a_circ;
+            for (int k = 0; k < n_circ; k++, ac += 32u) {
+                const double2 cxy = lds2(ac);
+                const double r2 = lds1(ac + 16u);
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    const double dx = X[j] - cxy.x, dy = Y[j] - cxy.y;
+                    const double h = fma(-dy, dy, fma(-dx, dx, r2));
+                    hit = hit || (act[j] && h > 0.0);
+                }
+            }
+            for (int k = 0; k < cfg.Ndynobs; k++) {
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    const uint32_t ae = a_ell + 48u * (k * N + (act[j] ? tix[j] : 0));
+                    const double2 exy = lds2(ae), csa = lds2(ae + 16u), ir = lds2(ae + 32u);
+                    const double dx = X[j] - exy.x, dy = Y[j] - exy.y;
+                    const double ea = fma(dx, csa.x, dy * csa.y);
+                    const double eb = fma(dx, csa.y, -(dy * csa.x));
+                    const double h = fma(-(eb * eb), ir.y, fma(-(ea * ea), ir.x, 1.0));
+                    hit = hit || (act[j] && h > 0.0);
+                }
+            }
+        }
+        if (__any_sync(FULL, hit)) {
+#else
+        {
+#endif
             uint32_t ac = a_circ;
             for (int k = 0; k < n_circ; k++, ac += 32u) {
                 const double2 cxy = lds2(ac);
@@ -718,7 +784,11 @@ enum Phase {
 };
 
 template <int P>
-__device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc_stats& st_out) {
+__device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc_stats& st_out, long long* prof_out = nullptr) {
+#ifdef NMPC_PROFILE
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tstart = clock64();
+#endif
     const nmpc_config& cfg = W.cfg;
     const int lane = W.lane;
     const int mem = cfg.lbfgs_memory, mem1 = cfg.lbfgs_memory + 1;
@@ -885,6 +955,9 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                     break;
                 }
                 // direction = H * fpr (two-loop recursion)
+#ifdef NMPC_PROFILE
+                const long long tl0 = clock64();
+#endif
                 double2 q[P];
 #pragma unroll
                 for (int j = 0; j < P; j++) q[j] = fpr[j];
@@ -923,6 +996,10 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                     }
                 }
                 W.st(V_DIR, q);
+#ifdef NMPC_PROFILE
+                prof[4] += clock64() - tl0;
+                prof[5]++;
+#endif
                 // linesearch(): right-hand side on the forward-backward envelope
                 {
                     double2 gs[P], uh[P];
@@ -973,6 +1050,11 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                 break;
             }
             case PH_EXIT: {
+#ifdef NMPC_PROFILE
+                prof[6] = clock64() - tstart;
+                if (prof_out && lane == 0)
+                    for (int i = 0; i < 8; i++) prof_out[i] = prof[i];
+#endif
                 st_out.exit_status = status;
                 st_out.outer_iterations = num_outer;
                 st_out.inner_iterations = inner_total;
@@ -992,7 +1074,16 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
 
         // ------------------------------------------------------------------ the one evaluation site
         pn_eval = (phase == PH_FINAL) ? make_pen(0.0) : pn;
+#ifdef NMPC_PROFILE
+        const long long tp0 = clock64();
+#endif
         const double psi = W.eval(mode, x, pn_eval, yl, g, pen, nullptr);
+#ifdef NMPC_PROFILE
+        {
+            const long long dt = clock64() - tp0;
+            if (mode == MODE_GRAD) { prof[0] += dt; prof[1]++; } else { prof[2] += dt; prof[3]++; }
+        }
+#endif
         if (mode == MODE_GRAD) n_grad++;
         if (mode == MODE_COST && phase != PH_FINAL) n_cost++;
 

@@ -13,8 +13,12 @@
 
 #include "nmpc_device.cuh"
 
+#ifndef NMPC_WARPS
+#define NMPC_WARPS 12  // warps (problems in flight) per SM; 32*NMPC_WARPS threads per CTA bounds the registers
+#endif
+
 template <int P>
-__global__ void __launch_bounds__(512, 1) nmpc_solve_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(32 * NMPC_WARPS, 1) nmpc_solve_kernel(const __grid_constant__ KArgs a) {
     const nmpc_config& cfg = a.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Lay L = make_layout(cfg.N_hor, cfg.Nobs, cfg.Ndynobs);
@@ -37,7 +41,11 @@ __global__ void __launch_bounds__(512, 1) nmpc_solve_kernel(const __grid_constan
         }
         nmpc_stats st;
         st.cost = 0.0;
+#ifdef NMPC_PROFILE
+        const int status = solve_problem<P>(W, u, yl, st, a.dbg ? a.dbg + (size_t)b * 8 : nullptr);
+#else
         const int status = solve_problem<P>(W, u, yl, st);
+#endif
 #pragma unroll
         for (int j = 0; j < P; j++) {
             const int t = lane + 32 * j;
@@ -58,7 +66,7 @@ __global__ void __launch_bounds__(512, 1) nmpc_solve_kernel(const __grid_constan
 
 // parity hook: psi, grad, F1, F2 for B (p, u, c, y) tuples
 template <int P>
-__global__ void __launch_bounds__(512, 1) nmpc_eval_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(32 * NMPC_WARPS, 1) nmpc_eval_kernel(const __grid_constant__ KArgs a) {
     const nmpc_config& cfg = a.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Lay L = make_layout(cfg.N_hor, cfg.Nobs, cfg.Ndynobs);
@@ -124,6 +132,10 @@ struct nmpc_handle {
     cudaEvent_t ev0, ev1;
     char err[512];
 };
+
+#ifdef NMPC_PROFILE
+static long long* g_dbg = nullptr;  // profiling builds only (scratch tooling, never shipped)
+#endif
 
 static int set_err(nmpc_handle* h, int code, const char* fmt, const char* detail) {
     if (h) snprintf(h->err, sizeof(h->err), fmt, detail ? detail : "");
@@ -217,7 +229,7 @@ int nmpc_create(const nmpc_config* cfg, int device, nmpc_handle** out) {
         delete h;
         return NMPC_ERR_INVALID;  // problem too large for one warp's arena
     }
-    if (w > 16) w = 16;
+    if (w > NMPC_WARPS) w = NMPC_WARPS;
     h->warps_per_cta = w;
     h->smem_bytes = per_warp * w;
     e = cudaFuncSetAttribute(solve_kernel_for(h->P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
@@ -278,6 +290,9 @@ static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU,
     a.status = dstatus;
     a.stats = dstats;
     a.counter = h->counter;
+#ifdef NMPC_PROFILE
+    a.dbg = g_dbg;
+#endif
     CUDA_TRY(h, cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), s));
     const int warps_needed = B;
     int grid = h->sm_count;
@@ -422,6 +437,10 @@ int nmpc_eval_batch(nmpc_handle* h, int32_t B, const double* P, const double* U,
     cudaFree(dP); cudaFree(dU); cudaFree(dY); cudaFree(dc); cudaFree(dpsi); cudaFree(dgrad); cudaFree(dF1); cudaFree(dF2);
     return rc;
 }
+
+#ifdef NMPC_PROFILE
+void nmpc_debug_set_buffer(void* p) { g_dbg = (long long*)p; }
+#endif
 
 int64_t nmpc_launch_count(nmpc_handle* h) { return h ? h->launches : 0; }
 double nmpc_last_kernel_ms(nmpc_handle* h) { return h ? h->last_ms : 0.0; }
