@@ -45,6 +45,18 @@ def eval_flops(N, Nobs, Nd):
     return N * (24 + 9 * Nobs + 16 * Nd + 18 * (N - 1)) + 10 * N
 
 
+def load_traffic(workload, batch):
+    """DRAM bytes per launch of the solve kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), if one matches this workload."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            for e in json.load(f)["captures"]:
+                if e["workload"] == workload and e["batch"] == batch:
+                    return e["dram_bytes_per_launch"]
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -189,13 +201,10 @@ def main():
     cfg = workloads.solver_config_for(hc)
     if world > 1:
         # the only collective on this path: the batch-invariant table (config scalars + cost weights)
-        # goes out from rank 0 over NCCL; every rank then checks its own copy against it.
-        table = torch.tensor([cfg.ts, cfg.lin_vel_min, cfg.lin_vel_max, cfg.ang_vel_max, cfg.lin_acc_min,
-                              cfg.lin_acc_max, cfg.ang_acc_max, cfg.tolerance] + [float(x) for x in P[0, 10:20]],
-                             dtype=torch.float64, device=dev)
-        mine = table.clone()
-        dist.broadcast(table, src=0)
-        assert torch.equal(table, mine), "static table differs across ranks"
+        # goes out from rank 0 over NCCL; every rank builds its solver from what it received.
+        from mpc_trajectory_generator_b200 import sharding
+        cfg, weights = sharding.broadcast_static_table(cfg, P[0, 10:20], device=dev, src=0)
+        P[:, 10:20] = np.asarray(weights)
     solver = pkg.NmpcSolver(cfg, device=local_rank)
     n2 = 2 * N
 
@@ -304,7 +313,7 @@ def main():
                     "ms_per_step": e2e_ms_step, "api": "NmpcSolver.solve_batch_into -> nmpc_solve_batch (C ABI), pinned host buffers"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
+                         "traffic": load_traffic(args.workload, B), "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
                          "algorithmic_bytes_per_solve": abytes,
                          "note": "latency/FP64-ALU bound by construction (4128 B vs ~1e8 flop per solve); "
                                  "see fp64 block and profiles/"},
