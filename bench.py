@@ -57,6 +57,13 @@ def load_traffic(workload, batch):
     return None
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -135,14 +142,14 @@ def run_reference(args, rank, world):
     oracle_c.build()
     P, U0, Y0, hc, desc = make_workload(args.workload, args.batch, args.seed)
     cfg = oracle_c.default_config(N_hor=hc.N_hor, Nobs=hc.Nobs, Ndynobs=hc.Ndynobs)
-    threads = oracle_c.max_threads()
+    threads = host_threads()   # torchrun pins OMP_NUM_THREADS=1; the CPU arm uses every host core it may run on
     sample = min(args.ref_sample, P.shape[0])
     Ps = P[:sample]
     for _ in range(args.warmup):
-        oracle_c.solve_batch(cfg, Ps[:min(32, sample)])
+        oracle_c.solve_batch(cfg, Ps[:min(32, sample)], nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, _, st, _ = oracle_c.solve_batch(cfg, Ps)
+        _, _, st, _ = oracle_c.solve_batch(cfg, Ps, nthreads=threads)
     dt = time.perf_counter() - t0
     val = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -329,14 +336,15 @@ def main():
             from oracle import oracle_c
             oracle_c.build()
             ocfg = oracle_c.default_config(N_hor=N, Nobs=Nobs, Ndynobs=Nd)
-            threads = oracle_c.max_threads()
+            threads = host_threads()   # torchrun pins OMP_NUM_THREADS=1; the CPU arm uses every host core it may run on
             t0 = time.perf_counter()
-            oracle_c.solve_batch(ocfg, P[:64], None if U0 is None else U0[:64], None if Y0 is None else Y0[:64])
+            oracle_c.solve_batch(ocfg, P[:64], None if U0 is None else U0[:64], None if Y0 is None else Y0[:64],
+                                 nthreads=threads)
             rate = 64 / (time.perf_counter() - t0)
             sample = int(min(B, max(64, rate * args.cpu_baseline_seconds)))
             t0 = time.perf_counter()
             Uo, Yo, sto, _ = oracle_c.solve_batch(ocfg, P[:sample], None if U0 is None else U0[:sample],
-                                                  None if Y0 is None else Y0[:sample])
+                                                  None if Y0 is None else Y0[:sample], nthreads=threads)
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"first {sample} problems of rank 0's batch, one pass, OpenMP over "

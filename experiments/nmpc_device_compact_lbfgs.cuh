@@ -57,7 +57,7 @@ enum { H_X0 = 0, H_Y0, H_TH0, H_VINIT, H_WINIT, H_XREF, H_YREF, H_THREF, H_Q, H_
 #define ELL_STRIDE 6   // ex ey | cosA sinA | 1/rx^2 1/ry^2
 
 struct Lay {
-    int n2, seg, circ, ell, rho, alpha, hdr, vref, total;
+    int n2, seg, circ, ell, rho, alpha, cco, gram, res, hdr, vref, total;
 };
 __host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
 __host__ __device__ inline Lay make_layout(int N, int Nobs, int Nd) {
@@ -69,6 +69,9 @@ __host__ __device__ inline Lay make_layout(int N, int Nobs, int Nd) {
     L.ell = o; o += ELL_STRIDE * Nd * N;
     L.rho = o; o += 12;
     L.alpha = o; o += 12;
+    L.cco = o; o += 12;
+    L.gram = o; o += 2 * MEMP1 * MEMP1;  // SY then YY, indexed by physical ring slot
+    L.res = o; o += 64;                  // results of the batched dot products of one PANOC iteration
     L.hdr = o; o += H_COUNT;
     L.vref = o; o += even_up(N);
     L.total = o;
@@ -304,6 +307,36 @@ __device__ __forceinline__ double wdiff2(const double2 (&a)[P], const double2 (&
     return hsum<P>(e);
 }
 
+
+// Transposed warp reduction of 32 per-lane values: on return lane l holds, in v[0], the sum over the 32
+// lanes of value l, accumulated in the same order as butterfly() (xor 16, 8, 4, 2, 1 — bit-identical to it).
+// 31 exchanges for 32 inner products instead of 160; each stage issues all its shuffles back to back.
+__device__ __forceinline__ void treduce32(double (&v)[32], const int lane) {
+#pragma unroll
+    for (int D = 16; D >= 1; D >>= 1) {
+        const bool hi = (lane & D) != 0;
+        double recv[16];
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const double send = hi ? v[k] : v[k + D];
+            recv[k] = __shfl_xor_sync(FULL, send, D);
+        }
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const double keep = hi ? v[k + D] : v[k];
+            v[k] = keep + recv[k];
+        }
+    }
+}
+// per-lane partial of a 2N-vector inner product (what hsum() would butterfly)
+template <int P>
+__device__ __forceinline__ double pdot(const double2 (&a)[P], const double2 (&b)[P]) {
+    double e = fma(a[0].y, b[0].y, a[0].x * b[0].x);
+#pragma unroll
+    for (int j = 1; j < P; j++) e = e + fma(a[j].y, b[j].y, a[j].x * b[j].x);
+    return e;
+}
+
 // ---------------------------------------------------------------------------------
 enum { MODE_COST = 0, MODE_GRAD = 1, MODE_F2 = 2 };
 struct Pen {
@@ -324,7 +357,7 @@ struct Warp {
     uint32_t sb;         // shared byte address of the arena
     uint32_t la[P];      // sb + 16*t : this lane's element inside vector 0
     uint32_t vstride;    // bytes per vector (2N doubles)
-    uint32_t a_seg, a_circ, a_ell, a_rho, a_alpha, a_hdr, a_vref;
+    uint32_t a_seg, a_circ, a_ell, a_rho, a_alpha, a_cco, a_gram, a_res, a_hdr, a_vref;
     int lane, n_circ;    // n_circ: circles with r != 0 (zero-padded slots are skipped: they add exact zeros)
     bool act[P];
     int tix[P];
@@ -334,6 +367,7 @@ struct Warp {
         vstride = (uint32_t)L.n2 * 8u;
         a_seg = sb + L.seg * 8u; a_circ = sb + L.circ * 8u; a_ell = sb + L.ell * 8u; a_rho = sb + L.rho * 8u;
         a_alpha = sb + L.alpha * 8u; a_hdr = sb + L.hdr * 8u; a_vref = sb + L.vref * 8u;
+        a_cco = sb + L.cco * 8u; a_gram = sb + L.gram * 8u; a_res = sb + L.res * 8u;
         n_circ = 0;
 #pragma unroll
         for (int j = 0; j < P; j++) {
@@ -847,6 +881,86 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
         int s = lb_head + i;
         return (s >= mem1) ? s - mem1 : s;
     };
+    auto RES = [&](int i) { return lds1(W.a_res + 8u * i); };
+    // RES index of the c-th inner product of stored pair i (see batch_dots)
+    auto RIX = [&](int i, int c) { return (i < 4) ? 9 + 5 * i + c : 32 + 5 * (i - 4) + c; };
+    // All inner products of one PANOC iteration as ONE batched reduction (results -> RES(i)):
+    //   0 fpr.fpr  1 grad.fpr  2 grad.grad  3 |gstep-uhalf|^2  4 s.y  5 s.s  6 y.y  7 s.fpr  8 y.fpr
+    //   RIX(i, c) for stored pair i:  c = 0 s_i.fpr  1 y_i.fpr  2 s.y_i  3 s_i.y  4 y.y_i   (s = u-old_state, y = fpr-old_g)
+    // Values are bit-identical to wdot()/wdiff2() of the same vectors (same lane partials, same butterfly order).
+    auto batch_dots = [&](const double2(&fpr)[P], const double2(&uh)[P]) {
+#ifdef NMPC_PROFILE
+        const long long tb0 = clock64();
+#endif
+        const int kact = lb_active;
+        const bool pair = !lb_first;
+        double2 sv[P], yv[P];
+        double v[32];
+        {
+            double2 gr[P], gs[P];
+            W.ld(V_GRAD, gr);
+            W.ld(V_GSTEP, gs);
+            v[0] = pdot<P>(fpr, fpr);
+            v[1] = pdot<P>(gr, fpr);
+            v[2] = pdot<P>(gr, gr);
+            double e = 0.0;
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                double d0 = gs[j].x - uh[j].x, d1 = gs[j].y - uh[j].y;
+                double ej = fma(d1, d1, d0 * d0);
+                e = (j == 0) ? ej : e + ej;
+            }
+            v[3] = e;
+        }
+        if (pair) {
+            double2 os[P], og[P];
+            W.ld(V_OLDS, os);
+            W.ld(V_OLDG, og);
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                sv[j] = make_double2(u[j].x - os[j].x, u[j].y - os[j].y);
+                yv[j] = make_double2(fpr[j].x - og[j].x, fpr[j].y - og[j].y);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < P; j++) sv[j] = yv[j] = make_double2(0.0, 0.0);
+        }
+        v[4] = pdot<P>(sv, yv);
+        v[5] = pdot<P>(sv, sv);
+        v[6] = pdot<P>(yv, yv);
+        v[7] = pdot<P>(sv, fpr);
+        v[8] = pdot<P>(yv, fpr);
+        auto pair_dots = [&](int i, double& p0, double& p1, double& p2, double& p3, double& p4) {
+            p0 = p1 = p2 = p3 = p4 = 0.0;
+            if (i < kact) {
+                double2 si[P], yi[P];
+                const int sl = slot(i);
+                W.ld(V_S + sl, si);
+                W.ld(V_Y + sl, yi);
+                p0 = pdot<P>(si, fpr);
+                p1 = pdot<P>(yi, fpr);
+                p2 = pdot<P>(sv, yi);
+                p3 = pdot<P>(si, yv);
+                p4 = pdot<P>(yv, yi);
+            }
+        };
+#pragma unroll
+        for (int i = 0; i < 4; i++) pair_dots(i, v[9 + 5 * i], v[10 + 5 * i], v[11 + 5 * i], v[12 + 5 * i], v[13 + 5 * i]);
+        v[29] = v[30] = v[31] = 0.0;
+        treduce32(v, lane);
+        sts1(W.a_res + 8u * lane, v[0]);
+        if (kact > 4) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) pair_dots(4 + i, v[5 * i], v[5 * i + 1], v[5 * i + 2], v[5 * i + 3], v[5 * i + 4]);
+            v[30] = v[31] = 0.0;
+            treduce32(v, lane);
+            sts1(W.a_res + 8u * (32 + lane), v[0]);
+        }
+        __syncwarp();
+#ifdef NMPC_PROFILE
+        prof[7] += clock64() - tb0;
+#endif
+    };
 
     for (;;) {
         // ------------------------------------------------------------------ pre: pick (x, mode)
@@ -870,12 +984,17 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                 break;
             }
             case PH_STEP_BEGIN: {
-                double2 gr[P], uh[P], fpr[P];
-                W.ld(V_GRAD, gr);
+                double2 uh[P], fpr[P];
                 W.ld(V_UHALF, uh);
-                compute_fpr(uh, fpr);
+#pragma unroll
+                for (int j = 0; j < P; j++) fpr[j] = make_double2(u[j].x - uh[j].x, u[j].y - uh[j].y);
+                W.st(V_FPR, fpr);
+                batch_dots(fpr, uh);  // every inner product this iteration needs, in one batched reduction
+                norm_fpr = sqrt(RES(0));
                 bool exit_now = false;
                 if (norm_fpr < cfg.tolerance) {
+                    double2 gr[P];
+                    W.ld(V_GRAD, gr);
                     double e[P];
 #pragma unroll
                     for (int j = 0; j < P; j++) {
@@ -890,7 +1009,6 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                     phase = PH_SOLVE_END;
                     continue;
                 }
-                W.st(V_FPR, fpr);
                 it_lip = 0;
 #pragma unroll
                 for (int j = 0; j < P; j++) x[j] = uh[j];
@@ -899,10 +1017,7 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                 break;
             }
             case PH_LIP_LOOP: {
-                double2 gr[P], fpr[P];
-                W.ld(V_GRAD, gr);
-                W.ld(V_FPR, fpr);
-                const double ip = wdot<P>(gr, fpr);
+                const double ip = RES(1);
                 const double rhs = cost + LIPSCHITZ_UPDATE_EPSILON * fabs(cost) - ip +
                                    (GAMMA_L_COEFF * 0.5 * inv_gamma) * (norm_fpr * norm_fpr);
                 if (cost_half > rhs && it_lip < MAX_LIPSCHITZ_UPDATE_ITERATIONS && lip < MAX_LIPSCHITZ_CONSTANT) {
@@ -910,7 +1025,8 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                     lb_first = 1;
                     lip *= 2.0;
                     set_gamma(gamma / 2.0);
-                    double2 gs[P], uh[P];
+                    double2 gr[P], gs[P], uh[P];
+                    W.ld(V_GRAD, gr);
                     grad_step_half(u, gr, gs, uh);
 #pragma unroll
                     for (int j = 0; j < P; j++) x[j] = uh[j];
@@ -919,37 +1035,56 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                     break;
                 }
                 sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * gamma);
-                // lbfgs_direction(): update_hessian(g = fpr, state = u)
+                double2 fpr[P];
+                W.ld(V_FPR, fpr);
+                // lbfgs_direction(): update_hessian(g = fpr, state = u) with the batched ys, ss, yy
+                const int k_old = lb_active;
+                bool have_new = false;
                 if (lb_first) {
                     lb_first = 0;
                     W.st(V_OLDS, u);
                     W.st(V_OLDG, fpr);
                 } else {
-                    double2 os[P], og[P], s[P], y[P];
-                    W.ld(V_OLDS, os);
-                    W.ld(V_OLDG, og);
-#pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        s[j] = make_double2(u[j].x - os[j].x, u[j].y - os[j].y);
-                        y[j] = make_double2(fpr[j].x - og[j].x, fpr[j].y - og[j].y);
-                    }
-                    const int tmp = slot(mem);
-                    W.st(V_S + tmp, s);
-                    W.st(V_Y + tmp, y);
-                    const double ys = wdot<P>(s, y), ss = wdot<P>(s, s);
+                    const double ys = RES(4), ss = RES(5), yy = RES(6);
                     const double rho_new = 1.0 / ys;
                     bool accept = !(ss <= DBL_EPS || ys <= SY_EPSILON);
                     if (accept) {
-                        const double lhs = ys / ss, rhsb = CBFGS_EPSILON * sqrt(wdot<P>(fpr, fpr));
+                        const double lhs = ys / ss, rhsb = CBFGS_EPSILON * sqrt(RES(0));
                         accept = (lhs > rhsb && isfinite(lhs) && isfinite(rhsb));
                     }
                     if (accept) {
+                        double2 os[P], og[P], sv[P], yv[P];
+                        W.ld(V_OLDS, os);
+                        W.ld(V_OLDG, og);
+#pragma unroll
+                        for (int j = 0; j < P; j++) {
+                            sv[j] = make_double2(u[j].x - os[j].x, u[j].y - os[j].y);
+                            yv[j] = make_double2(fpr[j].x - og[j].x, fpr[j].y - og[j].y);
+                        }
+                        const int tmp = slot(mem);
+                        W.st(V_S + tmp, sv);
+                        W.st(V_Y + tmp, yv);
                         W.st(V_OLDS, u);
                         W.st(V_OLDG, fpr);
-                        if (lane == 0) sts1(W.a_rho + 8u * tmp, rho_new);
+                        // Gram rows/columns of the new pair: lane i copies the three entries against old pair i
+                        if (lane < k_old) {
+                            const int pi = slot(lane);
+                            const double sy_new_i = RES(RIX(lane, 2)), sy_i_new = RES(RIX(lane, 3));
+                            const double yy_i = RES(RIX(lane, 4));
+                            sts1(W.a_gram + 8u * (tmp * MEMP1 + pi), sy_new_i);
+                            sts1(W.a_gram + 8u * (pi * MEMP1 + tmp), sy_i_new);
+                            sts1(W.a_gram + 8u * (MEMP1 * MEMP1 + tmp * MEMP1 + pi), yy_i);
+                            sts1(W.a_gram + 8u * (MEMP1 * MEMP1 + pi * MEMP1 + tmp), yy_i);
+                        }
+                        if (lane == 0) {
+                            sts1(W.a_gram + 8u * (tmp * MEMP1 + tmp), ys);
+                            sts1(W.a_gram + 8u * (MEMP1 * MEMP1 + tmp * MEMP1 + tmp), yy);
+                            sts1(W.a_rho + 8u * tmp, rho_new);
+                        }
                         lb_head = (lb_head + mem >= mem1) ? lb_head + mem - mem1 : lb_head + mem;
-                        lb_gamma = (1.0 / rho_new) / wdot<P>(y, y);
+                        lb_gamma = (1.0 / rho_new) / yy;
                         lb_active = (lb_active + 1 < mem) ? lb_active + 1 : mem;
+                        have_new = true;
                         __syncwarp();
                     }
                 }
@@ -961,59 +1096,83 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                     phase = PH_IT0;
                     break;
                 }
-                // direction = H * fpr (two-loop recursion)
+                // direction = H * fpr: two-loop recursion in compact form (scalar recursion on the Gram entries)
 #ifdef NMPC_PROFILE
                 const long long tl0 = clock64();
 #endif
                 double2 q[P];
-#pragma unroll
-                for (int j = 0; j < P; j++) q[j] = fpr[j];
-                if (lb_active > 0) {
-                    for (int k = 0; k < lb_active; k++) {
-                        const int sl = slot(k);
-                        double2 s[P], y[P];
-                        W.ld(V_S + sl, s);
-                        W.ld(V_Y + sl, y);
-                        const double al = lds1(W.a_rho + 8u * sl) * wdot<P>(s, q);
-                        if (lane == 0) sts1(W.a_alpha + 8u * k, al);
-#pragma unroll
-                        for (int j = 0; j < P; j++) {
-                            q[j].x = fma(-al, y[j].x, q[j].x);
-                            q[j].y = fma(-al, y[j].y, q[j].y);
-                        }
+                const int k = lb_active;
+                if (k > 0) {
+                    // Lane i owns stored pair i (new logical order: 0 = the pair just accepted, if any).
+                    //   forward solve :  alpha_j = rho_j acc_j ;  acc_i -= alpha_j s_i.y_j (i > j) ;  t_i -= alpha_j y_i.y_j
+                    //   backward solve:  c_l = alpha_l - rho_l t_l ;  t_i += c_l s_l.y_i (i < l)        (t_i scaled by gamma between)
+                    // one shuffle + one fma per step instead of a 40-element reduction per step.
+                    const bool mine = lane < k;
+                    const int li = mine ? lane : 0;
+                    const int pi = slot(li);
+                    const int ri = have_new ? (li == 0 ? 7 : RIX(li - 1, 0)) : RIX(li, 0);  // RES index of s_i.fpr (y_i.fpr follows)
+                    double acc = RES(ri), t = RES(ri + 1);
+                    const double rho_i = lds1(W.a_rho + 8u * pi);
+                    const uint32_t row_sy = W.a_gram + 8u * (pi * MEMP1);                    // s_i.y_*
+                    const uint32_t row_yy = W.a_gram + 8u * (MEMP1 * MEMP1 + pi * MEMP1);    // y_i.y_*
+                    const uint32_t col_sy = W.a_gram + 8u * pi;                              // s_*.y_i
+                    double al_i = 0.0, c_i = 0.0;
+                    for (int j = 0; j < k; j++) {
+                        const int pj = slot(j);
+                        const double alj = __shfl_sync(FULL, rho_i * acc, j);
+                        if (lane == j) al_i = alj;
+                        const double syij = lds1(row_sy + 8u * pj), yyij = lds1(row_yy + 8u * pj);
+                        if (lane > j) acc = fma(-alj, syij, acc);
+                        t = fma(-alj, yyij, t);
+                    }
+                    t = lb_gamma * t;
+                    for (int l = k - 1; l >= 0; l--) {
+                        const int pl = slot(l);
+                        const double cl = __shfl_sync(FULL, al_i - rho_i * t, l);
+                        if (lane == l) c_i = cl;
+                        const double syli = lds1(col_sy + 8u * (pl * MEMP1));
+                        if (lane < l) t = fma(cl, syli, t);
+                    }
+                    if (mine) {
+                        sts1(W.a_alpha + 8u * lane, al_i);
+                        sts1(W.a_cco + 8u * lane, c_i);
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        q[j].x = q[j].x * lb_gamma;
-                        q[j].y = q[j].y * lb_gamma;
-                    }
-                    for (int k = lb_active - 1; k >= 0; k--) {
-                        const int sl = slot(k);
-                        double2 s[P], y[P];
-                        W.ld(V_S + sl, s);
-                        W.ld(V_Y + sl, y);
-                        const double beta = lds1(W.a_rho + 8u * sl) * wdot<P>(y, q);
-                        const double co = lds1(W.a_alpha + 8u * k) - beta;
+                    for (int j = 0; j < P; j++) q[j] = make_double2(lb_gamma * fpr[j].x, lb_gamma * fpr[j].y);
+                    for (int jj = 0; jj < k; jj++) {
+                        const double co = -(lb_gamma * lds1(W.a_alpha + 8u * jj));
+                        double2 yv[P];
+                        W.ld(V_Y + slot(jj), yv);
 #pragma unroll
                         for (int j = 0; j < P; j++) {
-                            q[j].x = fma(co, s[j].x, q[j].x);
-                            q[j].y = fma(co, s[j].y, q[j].y);
+                            q[j].x = fma(co, yv[j].x, q[j].x);
+                            q[j].y = fma(co, yv[j].y, q[j].y);
                         }
                     }
+                    for (int l = k - 1; l >= 0; l--) {
+                        const double co = lds1(W.a_cco + 8u * l);
+                        double2 sv[P];
+                        W.ld(V_S + slot(l), sv);
+#pragma unroll
+                        for (int j = 0; j < P; j++) {
+                            q[j].x = fma(co, sv[j].x, q[j].x);
+                            q[j].y = fma(co, sv[j].y, q[j].y);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < P; j++) q[j] = fpr[j];
                 }
                 W.st(V_DIR, q);
 #ifdef NMPC_PROFILE
                 prof[4] += clock64() - tl0;
                 prof[5]++;
 #endif
-                // linesearch(): right-hand side on the forward-backward envelope
+                // linesearch(): right-hand side on the forward-backward envelope (gg, dist2 from the batch)
                 {
-                    double2 gs[P], uh[P];
-                    W.ld(V_GSTEP, gs);
-                    W.ld(V_UHALF, uh);
-                    const double dist2 = wdiff2<P>(gs, uh);
-                    const double fbe = cost - (0.5 * gamma) * wdot<P>(gr, gr) + (0.5 * dist2) * inv_gamma;
+                    const double dist2 = RES(3), gg = RES(2);
+                    const double fbe = cost - (0.5 * gamma) * gg + (0.5 * dist2) * inv_gamma;
                     rhs_ls = fbe - sigma * (norm_fpr * norm_fpr);
                 }
                 tau = 1.0;
@@ -1149,8 +1308,11 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                 cost_half = psi;
                 double2 uh[P], fpr[P];
                 W.ld(V_UHALF, uh);
-                compute_fpr(uh, fpr);
+#pragma unroll
+                for (int j = 0; j < P; j++) fpr[j] = make_double2(u[j].x - uh[j].x, u[j].y - uh[j].y);
                 W.st(V_FPR, fpr);
+                batch_dots(fpr, uh);  // gamma changed: every batched inner product is recomputed
+                norm_fpr = sqrt(RES(0));
                 it_lip++;
                 phase = PH_LIP_LOOP;
                 break;

@@ -453,6 +453,8 @@ typedef struct {
     double lgamma;
     double s[MEMP1][2 * MAXT], y[MEMP1][2 * MAXT];
     double rho[MEMP1], alpha[NMPC_LBFGS_MAX];
+    double SY[MEMP1][MEMP1], YY[MEMP1][MEMP1]; /* Gram entries s_p.y_q, y_p.y_q by physical slot */
+    int two_loop;                               /* 1 (default): literal two-loop recursion; 0: compact form */
     double old_state[2 * MAXT], old_g[2 * MAXT];
 } lbfgs_t;
 
@@ -480,13 +482,26 @@ static void lb_update(lbfgs_t* L, const double* g, const double* state) {
     if (!(lhs > rhs && isfinite(lhs) && isfinite(rhs))) return;
     memcpy(L->old_state, state, n2 * sizeof(double));
     memcpy(L->old_g, g, n2 * sizeof(double));
+    /* Gram rows/columns of the new pair against the pairs currently held (compact form, see lb_apply) */
+    double yy = vdot(y, y, L->N, L->P);
+    for (int k = 0; k < L->active; k++) {
+        int p = lb_slot(L, k);
+        L->SY[tmp][p] = vdot(s, L->y[p], L->N, L->P);
+        L->SY[p][tmp] = vdot(L->s[p], y, L->N, L->P);
+        double v = vdot(y, L->y[p], L->N, L->P);
+        L->YY[tmp][p] = v;
+        L->YY[p][tmp] = v;
+    }
+    L->SY[tmp][tmp] = ys;
+    L->YY[tmp][tmp] = yy;
     L->head = (L->head + L->mem) % (L->mem + 1); /* rotate_right(1): staging slot becomes slot 0 */
-    L->lgamma = (1.0 / L->rho[tmp]) / vdot(y, y, L->N, L->P);
+    L->lgamma = (1.0 / L->rho[tmp]) / yy;
     L->active = (L->active + 1 < L->mem) ? L->active + 1 : L->mem;
 }
 
-static void lb_apply(lbfgs_t* L, double* q) {
-    if (L->active == 0) return;
+/* literal two-loop recursion of the lbfgs crate (Lbfgs::apply_hessian): 2*active sequential reductions.
+ * This is the arithmetic contract shared with the kernel. */
+static void lb_apply_two_loop(lbfgs_t* L, double* q) {
     const int n2 = L->n2;
     for (int k = 0; k < L->active; k++) {
         int sl = lb_slot(L, k);
@@ -500,6 +515,45 @@ static void lb_apply(lbfgs_t* L, double* q) {
         double beta = L->rho[sl] * vdot(L->y[sl], q, L->N, L->P);
         double co = L->alpha[k] - beta;
         for (int i = 0; i < n2; i++) q[i] = fma(co, L->s[sl][i], q[i]);
+    }
+}
+
+/* Lbfgs::apply_hessian in compact form — an ALTERNATIVE evaluation order kept for sensitivity tests
+ * (NMPC_ORACLE_COMPACT=1) and for experiments/nmpc_device_compact_lbfgs.cuh; NOT the default.  Same two-loop
+ * recursion, but every inner product is taken against the ORIGINAL g and the stored pairs, so they are all
+ * independent (one batched warp reduction on the GPU) and the recursion itself runs on scalars:
+ *   alpha_i = rho_i (s_i.g - sum_{j<i} alpha_j s_i.y_j)
+ *   beta_i  = rho_i (gamma (y_i.g - sum_j alpha_j y_i.y_j) + sum_{l>i} c_l s_l.y_i),   c_i = alpha_i - beta_i
+ *   d       = gamma g - sum_j gamma alpha_j y_j + sum_l c_l s_l
+ * Mathematically identical to lb_apply_two_loop; differs in rounding only. */
+static void lb_apply(lbfgs_t* L, double* q) {
+    if (L->active == 0) return;
+    if (L->two_loop) { lb_apply_two_loop(L, q); return; }
+    const int n2 = L->n2, k = L->active;
+    int p[NMPC_LBFGS_MAX];
+    double a[NMPC_LBFGS_MAX], b[NMPC_LBFGS_MAX], al[NMPC_LBFGS_MAX], c[NMPC_LBFGS_MAX];
+    for (int i = 0; i < k; i++) {
+        p[i] = lb_slot(L, i);
+        a[i] = vdot(L->s[p[i]], q, L->N, L->P);
+        b[i] = vdot(L->y[p[i]], q, L->N, L->P);
+    }
+    for (int i = 0; i < k; i++) {
+        double acc = a[i];
+        for (int j = 0; j < i; j++) acc = fma(-al[j], L->SY[p[i]][p[j]], acc);
+        al[i] = L->rho[p[i]] * acc;
+    }
+    for (int i = k - 1; i >= 0; i--) {
+        double t = b[i];
+        for (int j = 0; j < k; j++) t = fma(-al[j], L->YY[p[i]][p[j]], t);
+        t = L->lgamma * t;
+        for (int l = k - 1; l > i; l--) t = fma(c[l], L->SY[p[l]][p[i]], t);
+        c[i] = al[i] - L->rho[p[i]] * t;
+    }
+    for (int e = 0; e < n2; e++) {
+        double acc = L->lgamma * q[e];
+        for (int j = 0; j < k; j++) acc = fma(-(L->lgamma * al[j]), L->y[p[j]][e], acc);
+        for (int l = k - 1; l >= 0; l--) acc = fma(c[l], L->s[p[l]][e], acc);
+        q[e] = acc;
     }
 }
 
@@ -669,6 +723,7 @@ int nmpc_oracle_solve(const nmpc_config* cfg, const double* p, double* u, double
     if (!y) { memset(ybuf, 0, sizeof(ybuf)); y = ybuf; }
     C->S = &S; C->n2 = n2; C->y = y;
     C->lb.n2 = n2; C->lb.N = N; C->lb.P = P; C->lb.mem = S.mem; C->lb.head = 0;
+    C->lb.two_loop = getenv("NMPC_ORACLE_COMPACT") == NULL; /* default: the literal two-loop recursion */
     C->tol = cfg->tolerance;
     C->c = cfg->initial_penalty;
     C->akkt_tol = cfg->initial_tolerance;

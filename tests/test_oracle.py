@@ -140,3 +140,28 @@ def test_recorded_reference_run_regression(oracle):
         u, y = U, Y
     # the recorded closed loop reached the goal of src/visibility/graphs.py:43 within the reference's tolerance
     assert abs(g["xx"][-1] - 19.0) < 0.05 and abs(g["xy"][-1] - 10.0) < 0.05
+
+
+def test_lbfgs_compact_form_agrees_with_two_loop():
+    """The L-BFGS direction can be evaluated in compact (Gram-matrix) form instead of the literal two-loop
+    recursion (an experiment for the GPU, experiments/): same flags, converged solutions equal to solver
+    tolerance.  Run in subprocesses because the switch is an environment variable read by the oracle."""
+    import subprocess
+    import sys
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r); import nmpc_problems as p; "
+            "from oracle import oracle_c as oc; cfg = oc.default_config(); "
+            "P = p.synth(20, 10, 3, 24, seed=5, active=False); U, Y, st, s = oc.solve_batch(cfg, P); "
+            "np.save(sys.argv[1], U); np.save(sys.argv[2], st)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = code % (root, os.path.join(root, "tests"))
+    out = {}
+    for name, env in (("two_loop", {}), ("compact", {"NMPC_ORACLE_COMPACT": "1"})):
+        fu, fs = f"/tmp/_lb_{name}_u.npy", f"/tmp/_lb_{name}_s.npy"
+        subprocess.check_call([sys.executable, "-c", code, fu, fs], env=dict(os.environ, **env))
+        out[name] = (np.load(fu), np.load(fs))
+    (Ua, sa), (Ub, sb) = out["two_loop"], out["compact"]
+    assert np.array_equal(sa, sb)
+    conv = sa == 0
+    assert conv.any()
+    rel = np.linalg.norm(Ua[conv] - Ub[conv], axis=1) / np.linalg.norm(Ua[conv], axis=1)
+    assert rel.max() < 1e-4
