@@ -9,6 +9,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "nmpc_kernels.cu")
+DEV = os.path.join(_HERE, "csrc", "nmpc_device.cuh")
 HDR = os.path.join(os.path.dirname(_HERE), "include", "nmpc_b200.h")
 LIB = os.path.join(_HERE, "libnmpc_b200.so")
 
@@ -27,16 +28,22 @@ def is_stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(f) > t for f in (SRC, HDR))
+    return any(os.path.getmtime(f) > t for f in (SRC, DEV, HDR))
 
 
 def build_library(force=False, verbose=False):
     """Compile the CUDA library if missing or older than its sources; returns its path."""
     if not force and not is_stale():
         return LIB
+    return build_variant(LIB, verbose=verbose)
+
+
+def build_variant(out, defines=(), verbose=False):
+    """Compile csrc/ into `out` with extra -D defines (tools/: profiling and tuning builds)."""
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libnmpc_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
+    cmd = ([nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+           + ["-o", out, SRC])
     subprocess.check_call(cmd)
-    return LIB
+    return out

@@ -29,6 +29,12 @@
 #ifndef NMPC_CTE_STAGE
 #define NMPC_CTE_STAGE 0
 #endif
+#ifndef NMPC_LB_PREFETCH
+#define NMPC_LB_PREFETCH 1
+#endif
+#ifndef NMPC_ICLAMP
+#define NMPC_ICLAMP 0  // measured neutral on B200 (round 1); the compare-select form is the oracle's
+#endif
 #define MEMP1 (NMPC_LBFGS_MAX + 1)
 
 // OpEn PANOC constants (panoc_engine.rs) — see oracle/nmpc_oracle.c for the restatement notes
@@ -51,7 +57,9 @@ extern __shared__ __align__(16) double smem[];
 // per-warp shared-memory arena (offsets in doubles; every block is 16-byte aligned)
 enum { V_GRAD = 0, V_UHALF, V_FPR, V_DIR, V_GSTEP, V_OLDS, V_OLDG, V_S, V_Y = V_S + MEMP1, V_END = V_Y + MEMP1 };
 enum { H_X0 = 0, H_Y0, H_TH0, H_VINIT, H_WINIT, H_XREF, H_YREF, H_THREF, H_Q, H_QV, H_QTH, H_RV, H_RW, H_QN, H_QTHN,
-       H_QCTE, H_AP, H_WP, H_INVTS, H_COUNT = 20 };
+       H_QCTE, H_AP, H_WP, H_INVTS,
+       // warp-uniform solver state that is touched once per outer iteration (kept out of the registers)
+       H_F2N, H_DYN, H_F2NP, H_DYNP, H_NORMH, H_LIP, H_AKKT, H_COUNT = 26 };
 #define SEG_STRIDE 6   // s1x s1y | dx dy | inv pad
 #define CIRC_STRIDE 4  // cx cy | r2 (original slot index as int in the 4th double)
 #define ELL_STRIDE 6   // ex ey | cosA sinA | 1/rx^2 1/ry^2
@@ -87,8 +95,15 @@ struct KArgs {
     // eval kernel only
     const double* cvec;
     double *psi, *grad, *F1, *F2;
-    long long* dbg;  // NMPC_PROFILE builds only: 8 cycle counters per problem
+    long long* dbg;  // NMPC_PROFILE builds only: 16 cycle counters per problem
 };
+#ifdef NMPC_PROFILE
+#define PROF_BEGIN() long long plast_ = clock64()
+#define PROF_MARK(i) do { const long long t_ = clock64(); pt[i] += t_ - plast_; plast_ = t_; } while (0)
+#else
+#define PROF_BEGIN() do { } while (0)
+#define PROF_MARK(i) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------
 // explicit shared-memory access (32-bit shared addresses)
@@ -119,6 +134,24 @@ __device__ __forceinline__ double clampd(double x, double lo, double hi) { retur
 // (written as setp/selp PTX: the C ternaries get canonicalised to max.f64/min.f64, which sm_100
 //  expands into a ~12-instruction DSETP.MAX/FSEL/SEL/NaN-fix-up sequence each)
 __device__ __forceinline__ double sel_clamp01(double t) {
+#if NMPC_ICLAMP
+    // Same result as the two compare-selects for every non-NaN t, computed on the integer pipe from the
+    // high word (sign and exponent order doubles like signed integers for t >= 0): hi' = min(max(hi, 0), hi(1.0)),
+    // lo' = lo only while 0 <= hi < hi(1.0).  Two FP64-pipe compares and four selects become four ALU ops.
+    // (NaN: the selects give 0, this gives 0 or 1 by the sign bit; either way the distance stays NaN because
+    //  a NaN projection parameter comes from a NaN point, which is already in ex/ey.)
+    double r;
+    asm("{\n\t.reg .b32 lo, hi, h2;\n\t.reg .pred p;\n\t"
+        "mov.b64 {lo, hi}, %1;\n\t"
+        "max.s32 h2, hi, 0;\n\t"
+        "min.s32 h2, h2, 0x3FF00000;\n\t"
+        "setp.lt.u32 p, hi, 0x3FF00000;\n\t"
+        "selp.b32 lo, lo, 0, p;\n\t"
+        "mov.b64 %0, {lo, h2};\n\t}"
+        : "=d"(r)
+        : "d"(t));
+    return r;
+#else
     double r;
     asm("{\n\t.reg .pred p;\n\t"
         "setp.gt.f64 p, %1, 0d0000000000000000;\n\tselp.f64 %0, %1, 0d0000000000000000, p;\n\t"
@@ -126,6 +159,7 @@ __device__ __forceinline__ double sel_clamp01(double t) {
         : "=d"(r)
         : "d"(t));
     return r;
+#endif
 }
 // if (d2 < best) { best = d2; bi = idx; }  — strict '<': the first minimal segment keeps the gradient
 __device__ __forceinline__ void take_if_less(double d2, int idx, double& best, int& bi) {
@@ -202,6 +236,32 @@ __device__ __forceinline__ void hsum2(const double (&e)[P], const double (&f)[P]
     }
     se = a;
     sf = b;
+}
+// four sums at once
+template <int P>
+__device__ __forceinline__ void hsum4(const double (&e0)[P], const double (&e1)[P], const double (&e2)[P],
+                                      const double (&e3)[P], double& s0, double& s1, double& s2, double& s3) {
+    double a = e0[0], b = e1[0], c = e2[0], d = e3[0];
+#pragma unroll
+    for (int j = 1; j < P; j++) {
+        a = a + e0[j];
+        b = b + e1[j];
+        c = c + e2[j];
+        d = d + e3[j];
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        double ya = __shfl_xor_sync(FULL, a, off), yb = __shfl_xor_sync(FULL, b, off);
+        double yc = __shfl_xor_sync(FULL, c, off), yd = __shfl_xor_sync(FULL, d, off);
+        a = a + ya;
+        b = b + yb;
+        c = c + yc;
+        d = d + yd;
+    }
+    s0 = a;
+    s1 = b;
+    s2 = c;
+    s3 = d;
 }
 template <int P>
 __device__ __forceinline__ void prefix_scan(const double (&x)[P], double (&incl)[P], double (&excl)[P], int lane) {
@@ -318,7 +378,9 @@ __device__ __forceinline__ Pen make_pen(double c) {
 }
 
 // One warp's view of its problem: arena addresses + lane mapping.
-template <int P>
+// NF > 0: the horizon is a compile-time constant (NF == cfg.N_hor, checked by the host): the cross-track
+// loop is fully unrolled with a tree arg-min, so a lone warp (the tail of a small batch) gets ILP.
+template <int P, int NF = 0>
 struct Warp {
     const nmpc_config& cfg;
     uint32_t sb;         // shared byte address of the arena
@@ -328,6 +390,9 @@ struct Warp {
     int lane, n_circ;    // n_circ: circles with r != 0 (zero-padded slots are skipped: they add exact zeros)
     bool act[P];
     int tix[P];
+#ifdef NMPC_PROFILE
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cycles per eval section (tools/prof_cycles.py)
+#endif
 
     __device__ __forceinline__ Warp(const nmpc_config& c, const Lay& L, int warp, int lane_) : cfg(c), lane(lane_) {
         sb = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)(warp * L.total) * 8u;
@@ -338,7 +403,7 @@ struct Warp {
 #pragma unroll
         for (int j = 0; j < P; j++) {
             tix[j] = lane + 32 * j;
-            act[j] = tix[j] < cfg.N_hor;
+            act[j] = tix[j] < (NF ? NF : cfg.N_hor);
             la[j] = sb + 16u * tix[j];
         }
     }
@@ -355,7 +420,7 @@ struct Warp {
 
     // unpack the parameter row (layout: include/nmpc_b200.h) into the arena
     __device__ void stage(const double* __restrict__ p) {
-        const int N = cfg.N_hor, Nobs = cfg.Nobs, Nd = cfg.Ndynobs;
+        const int N = NF ? NF : cfg.N_hor, Nobs = cfg.Nobs, Nd = cfg.Ndynobs;
         __syncwarp();
         if (lane < 8) sts1(a_hdr + 8u * lane, p[lane]);
         if (lane >= 8 && lane < 18) sts1(a_hdr + 8u * lane, p[lane + 2]);
@@ -428,8 +493,9 @@ struct Warp {
     __device__ double eval(const int mode, const double2 (&uv)[P], const Pen pn, const double2 (&yl)[P],
                            double2 (&gout)[P], double& pen_out, double* __restrict__ F2g) {
         const bool GRAD = (mode == MODE_GRAD);
-        const int N = cfg.N_hor;
+        const int N = NF ? NF : cfg.N_hor;
         const double ts = cfg.ts;
+        PROF_BEGIN();
         double tw[P], inclT[P], exclT[P];
 #pragma unroll
         for (int j = 0; j < P; j++) tw[j] = act[j] ? ts * uv[j].y : 0.0;
@@ -444,6 +510,7 @@ struct Warp {
             a[j] = act[j] ? ts * (uv[j].x * cs[j]) : 0.0;
             b[j] = act[j] ? ts * (uv[j].x * sn[j]) : 0.0;
         }
+        PROF_MARK(0);
         double X[P], Y[P], xpre[P], ypre[P];
         {
             double ia[P], ea[P], ib[P], eb[P];
@@ -461,6 +528,7 @@ struct Warp {
 #pragma unroll
         for (int j = 0; j < P; j++) gX[j] = gY[j] = mind2[j] = 0.0;
         const double qcte = hdr(H_QCTE);
+        PROF_MARK(1);
 
         if (mode != MODE_F2) {
             // cross-track error: each lane scans the N-1 segments for its own predicted point
@@ -471,6 +539,29 @@ struct Warp {
                 best[j] = CUDART_INF;
                 bi[j] = 1;
             }
+            if constexpr (NF > 0 && P == 1) {
+                // all NF-1 segments are independent; arg-min by a tree whose left operand holds the lower
+                // indices and wins ties (= the first minimal segment, as the serial strict-'<' scan)
+                double dv[NF - 1];
+                int iv[NF - 1];
+#pragma unroll
+                for (int i = 1; i < NF; i++) {
+                    const uint32_t as = a_seg + 48u * i;
+                    const double2 s1 = lds2(as), d = lds2(as + 16u);
+                    const double inv = lds1(as + 32u);
+                    double px = X[0] - s1.x, py = Y[0] - s1.y;
+                    double that = fma(px, d.x, py * d.y) * inv;
+                    double tst = sel_clamp01(that);
+                    double ex = fma(tst, d.x, -px), ey = fma(tst, d.y, -py);
+                    dv[i - 1] = fma(ex, ex, ey * ey);
+                    iv[i - 1] = i;
+                }
+#pragma unroll
+                for (int st = 1; st < NF - 1; st *= 2)
+#pragma unroll
+                    for (int k = 0; k + st < NF - 1; k += 2 * st) take_if_less(dv[k + st], iv[k + st], dv[k], iv[k]);
+                take_if_less(dv[0], iv[0], best[0], bi[0]);
+            } else {
             constexpr int UNR = (P == 1) ? 4 : 2;
             uint32_t as = a_seg + 48u;
             int i = 1;
@@ -540,6 +631,7 @@ struct Warp {
                     take_if_less(d2, i, best[j], bi[j]);
                 }
             }
+            }
 #pragma unroll
             for (int j = 0; j < P; j++) {
                 mind2[j] = best[j];
@@ -559,6 +651,7 @@ struct Warp {
             }
         }
 
+        PROF_MARK(2);
         // obstacle penalty F2: circles (non-padded ones), then this lane's time slice of each ellipse.
         // Obstacles are tested in chunks: all inside-tests and votes of a chunk are issued back to back and
         // ONE branch decides whether any of them needs the (rare) ordered time-sum + gradient path.
@@ -685,6 +778,7 @@ struct Warp {
             }
         }
         pen_out = pen;
+        PROF_MARK(3);
         if (mode == MODE_F2) return 0.0;
 
         // stage cost, acceleration cost, ALM term
@@ -731,6 +825,7 @@ struct Warp {
         const double eXN = XN - xref, eYN = YN - yref, eTN = TN - thref;
         const double term = fma(w_qN, fma(eXN, eXN, eYN * eYN), w_qthN * (eTN * eTN));
         const double psi = fma(pn.hc, pen, hsum<P>(cl) + term);
+        PROF_MARK(4);
         if (!GRAD) return psi;
 
         // backward sweep
@@ -778,6 +873,7 @@ struct Warp {
             double gw = fma(ts, TT[j], lw);
             gout[j] = act[j] ? make_double2(gv, gw) : make_double2(0.0, 0.0);
         }
+        PROF_MARK(5);
         return psi;
     }
 };
@@ -790,8 +886,8 @@ enum Phase {
     PH_STEP_DONE, PH_SOLVE_END, PH_F2, PH_FINAL, PH_EXIT
 };
 
-template <int P>
-__device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc_stats& st_out, long long* prof_out = nullptr) {
+template <int P, int NF>
+__device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], nmpc_stats& st_out, long long* prof_out = nullptr) {
 #ifdef NMPC_PROFILE
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long tstart = clock64();
@@ -801,15 +897,25 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
     const int mem = cfg.lbfgs_memory, mem1 = cfg.lbfgs_memory + 1;
     const int nf2 = cfg.Nobs + cfg.Ndynobs;
     // warp-uniform state
-    double gamma = 0.0, inv_gamma = 0.0, sigma = 0.0, lip = 0.0, cost = 0.0, norm_fpr = 0.0, tau = 1.0;
-    double akkt_tol = cfg.initial_tolerance, cost_half = 0.0, norm_h = 0.0, rhs_ls = 0.0, lb_gamma = 1.0;
+    double gamma = 0.0, inv_gamma = 0.0, sigma = 0.0, cost = 0.0, norm_fpr = 0.0, tau = 1.0;
+    double cost_half = 0.0, rhs_ls = 0.0, lb_gamma = 1.0;
+    // rarely touched warp-uniform scalars live in the arena header: every lane stores the same value and
+    // reads back its own store, so no synchronisation is involved
+    auto sget = [&](int i) { return lds1(W.a_hdr + 8u * i); };
+    auto sput = [&](int i, double v) { sts1(W.a_hdr + 8u * i, v); };
+    sput(H_AKKT, cfg.initial_tolerance);
+    sput(H_F2N, 0.0);
+    sput(H_DYN, 0.0);
+    sput(H_F2NP, 0.0);
+    sput(H_DYNP, 0.0);
+    sput(H_LIP, 0.0);
     Pen pn = make_pen(cfg.initial_penalty);
     Pen pn_eval = pn;
     int iteration = 0, n_cost = 0, n_grad = 0, lb_active = 0, lb_first = 1, lb_head = 0;
     int alm_iter = 0, inner_total = 0, num_outer = 0, status = NMPC_CONVERGED, inner_status = NMPC_CONVERGED;
     int num_iter = 0, it_lip = 0, nls = 0;
-    bool cont = true;
-    double f2n = 0.0, f2np = 0.0, dyn = 0.0, dynp = 0.0;
+    bool cont = true, fbe_valid = false;
+    double fbe_u = 0.0;
     const double inv_ts = W.hdr(H_INVTS);
 
     double2 x[P], g[P];  // evaluation point / gradient out
@@ -861,6 +967,7 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                 // panoc init
                 lb_active = 0;
                 lb_first = 1;
+                fbe_valid = false;
                 tau = 1.0;
                 iteration = 0;
 #pragma unroll
@@ -884,7 +991,7 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                         double r1 = fma(fpr[j].y, inv_gamma, gr[j].y) - p1;
                         e[j] = fma(r1, r1, r0 * r0);
                     }
-                    exit_now = sqrt(hsum<P>(e)) < akkt_tol;
+                    exit_now = sqrt(hsum<P>(e)) < sget(H_AKKT);
                 }
                 if (exit_now) {
                     phase = PH_SOLVE_END;
@@ -899,16 +1006,37 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                 break;
             }
             case PH_LIP_LOOP: {
-                double2 gr[P], fpr[P];
+                double2 gr[P], fpr[P], s[P], y[P];
                 W.ld(V_GRAD, gr);
                 W.ld(V_FPR, fpr);
-                const double ip = wdot<P>(gr, fpr);
+                // <grad, fpr> for the Lipschitz test and, when a previous (state, fpr) pair exists, the three
+                // inner products of the L-BFGS update (s.y, s.s, y.y) in ONE interleaved butterfly
+                double ip, ys = 0.0, ss = 0.0, yy = 0.0;
+                if (lb_first) {
+                    ip = wdot<P>(gr, fpr);
+                } else {
+                    double2 os[P], og[P];
+                    W.ld(V_OLDS, os);
+                    W.ld(V_OLDG, og);
+                    double e0[P], e1[P], e2[P], e3[P];
+#pragma unroll
+                    for (int j = 0; j < P; j++) {
+                        s[j] = make_double2(u[j].x - os[j].x, u[j].y - os[j].y);
+                        y[j] = make_double2(fpr[j].x - og[j].x, fpr[j].y - og[j].y);
+                        e0[j] = fma(gr[j].y, fpr[j].y, gr[j].x * fpr[j].x);
+                        e1[j] = fma(s[j].y, y[j].y, s[j].x * y[j].x);
+                        e2[j] = fma(s[j].y, s[j].y, s[j].x * s[j].x);
+                        e3[j] = fma(y[j].y, y[j].y, y[j].x * y[j].x);
+                    }
+                    hsum4<P>(e0, e1, e2, e3, ip, ys, ss, yy);
+                }
                 const double rhs = cost + LIPSCHITZ_UPDATE_EPSILON * fabs(cost) - ip +
                                    (GAMMA_L_COEFF * 0.5 * inv_gamma) * (norm_fpr * norm_fpr);
-                if (cost_half > rhs && it_lip < MAX_LIPSCHITZ_UPDATE_ITERATIONS && lip < MAX_LIPSCHITZ_CONSTANT) {
+                if (cost_half > rhs && it_lip < MAX_LIPSCHITZ_UPDATE_ITERATIONS && sget(H_LIP) < MAX_LIPSCHITZ_CONSTANT) {
                     lb_active = 0;
                     lb_first = 1;
-                    lip *= 2.0;
+                    fbe_valid = false;
+                    sput(H_LIP, sget(H_LIP) * 2.0);
                     set_gamma(gamma / 2.0);
                     double2 gs[P], uh[P];
                     grad_step_half(u, gr, gs, uh);
@@ -925,22 +1053,14 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                     W.st(V_OLDS, u);
                     W.st(V_OLDG, fpr);
                 } else {
-                    double2 os[P], og[P], s[P], y[P];
-                    W.ld(V_OLDS, os);
-                    W.ld(V_OLDG, og);
-#pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        s[j] = make_double2(u[j].x - os[j].x, u[j].y - os[j].y);
-                        y[j] = make_double2(fpr[j].x - og[j].x, fpr[j].y - og[j].y);
-                    }
                     const int tmp = slot(mem);
                     W.st(V_S + tmp, s);
                     W.st(V_Y + tmp, y);
-                    const double ys = wdot<P>(s, y), ss = wdot<P>(s, s);
                     const double rho_new = 1.0 / ys;
                     bool accept = !(ss <= DBL_EPS || ys <= SY_EPSILON);
                     if (accept) {
-                        const double lhs = ys / ss, rhsb = CBFGS_EPSILON * sqrt(wdot<P>(fpr, fpr));
+                        // sqrt(<fpr, fpr>) is norm_fpr: same vector, same expression, same reduction order
+                        const double lhs = ys / ss, rhsb = CBFGS_EPSILON * norm_fpr;
                         accept = (lhs > rhsb && isfinite(lhs) && isfinite(rhsb));
                     }
                     if (accept) {
@@ -948,7 +1068,7 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                         W.st(V_OLDG, fpr);
                         if (lane == 0) sts1(W.a_rho + 8u * tmp, rho_new);
                         lb_head = (lb_head + mem >= mem1) ? lb_head + mem - mem1 : lb_head + mem;
-                        lb_gamma = (1.0 / rho_new) / wdot<P>(y, y);
+                        lb_gamma = (1.0 / rho_new) / yy;
                         lb_active = (lb_active + 1 < mem) ? lb_active + 1 : mem;
                         __syncwarp();
                     }
@@ -968,18 +1088,68 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                 double2 q[P];
 #pragma unroll
                 for (int j = 0; j < P; j++) q[j] = fpr[j];
+#if NMPC_LB_PREFETCH
                 if (lb_active > 0) {
+                    // each step's (s, y) pair is fetched while the previous step's butterfly is in flight
+                    double2 sv[P], yv[P], sn[P], yn[P];
+                    int sl = slot(0);
+                    W.ld(V_S + sl, sv);
+                    W.ld(V_Y + sl, yv);
+                    double rho = lds1(W.a_rho + 8u * sl);
                     for (int k = 0; k < lb_active; k++) {
-                        const int sl = slot(k);
-                        double2 s[P], y[P];
-                        W.ld(V_S + sl, s);
-                        W.ld(V_Y + sl, y);
-                        const double al = lds1(W.a_rho + 8u * sl) * wdot<P>(s, q);
+                        const int sl_n = slot((k + 1 < lb_active) ? k + 1 : k);
+                        W.ld(V_S + sl_n, sn);
+                        W.ld(V_Y + sl_n, yn);
+                        const double rho_n = lds1(W.a_rho + 8u * sl_n);
+                        const double al = rho * wdot<P>(sv, q);
                         if (lane == 0) sts1(W.a_alpha + 8u * k, al);
 #pragma unroll
                         for (int j = 0; j < P; j++) {
-                            q[j].x = fma(-al, y[j].x, q[j].x);
-                            q[j].y = fma(-al, y[j].y, q[j].y);
+                            q[j].x = fma(-al, yv[j].x, q[j].x);
+                            q[j].y = fma(-al, yv[j].y, q[j].y);
+                            sv[j] = sn[j];
+                            yv[j] = yn[j];
+                        }
+                        rho = rho_n;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < P; j++) {
+                        q[j].x = q[j].x * lb_gamma;
+                        q[j].y = q[j].y * lb_gamma;
+                    }
+                    // (sv, yv, rho) now hold the newest pair (k = lb_active-1): the backward loop starts there
+                    for (int k = lb_active - 1; k >= 0; k--) {
+                        const int sl_n = slot((k > 0) ? k - 1 : 0);
+                        W.ld(V_S + sl_n, sn);
+                        W.ld(V_Y + sl_n, yn);
+                        const double rho_n = lds1(W.a_rho + 8u * sl_n);
+                        const double alk = lds1(W.a_alpha + 8u * k);
+                        const double beta = rho * wdot<P>(yv, q);
+                        const double co = alk - beta;
+#pragma unroll
+                        for (int j = 0; j < P; j++) {
+                            q[j].x = fma(co, sv[j].x, q[j].x);
+                            q[j].y = fma(co, sv[j].y, q[j].y);
+                            sv[j] = sn[j];
+                            yv[j] = yn[j];
+                        }
+                        rho = rho_n;
+                    }
+                }
+#else
+                if (lb_active > 0) {
+                    for (int k = 0; k < lb_active; k++) {
+                        const int sl = slot(k);
+                        double2 sv[P], yv[P];
+                        W.ld(V_S + sl, sv);
+                        W.ld(V_Y + sl, yv);
+                        const double al = lds1(W.a_rho + 8u * sl) * wdot<P>(sv, q);
+                        if (lane == 0) sts1(W.a_alpha + 8u * k, al);
+#pragma unroll
+                        for (int j = 0; j < P; j++) {
+                            q[j].x = fma(-al, yv[j].x, q[j].x);
+                            q[j].y = fma(-al, yv[j].y, q[j].y);
                         }
                     }
                     __syncwarp();
@@ -990,30 +1160,45 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                     }
                     for (int k = lb_active - 1; k >= 0; k--) {
                         const int sl = slot(k);
-                        double2 s[P], y[P];
-                        W.ld(V_S + sl, s);
-                        W.ld(V_Y + sl, y);
-                        const double beta = lds1(W.a_rho + 8u * sl) * wdot<P>(y, q);
+                        double2 sv[P], yv[P];
+                        W.ld(V_S + sl, sv);
+                        W.ld(V_Y + sl, yv);
+                        const double beta = lds1(W.a_rho + 8u * sl) * wdot<P>(yv, q);
                         const double co = lds1(W.a_alpha + 8u * k) - beta;
 #pragma unroll
                         for (int j = 0; j < P; j++) {
-                            q[j].x = fma(co, s[j].x, q[j].x);
-                            q[j].y = fma(co, s[j].y, q[j].y);
+                            q[j].x = fma(co, sv[j].x, q[j].x);
+                            q[j].y = fma(co, sv[j].y, q[j].y);
                         }
                     }
                 }
+#endif
                 W.st(V_DIR, q);
 #ifdef NMPC_PROFILE
                 prof[4] += clock64() - tl0;
                 prof[5]++;
 #endif
                 // linesearch(): right-hand side on the forward-backward envelope
-                {
+                if (fbe_valid) {
+                    // the envelope at u is the accepted trial's left-hand side of the previous line search
+                    // (same cost, gradient, gamma and stored gstep/uhalf: bit-identical), unless gamma changed
+                    rhs_ls = fbe_u - sigma * (norm_fpr * norm_fpr);
+                } else {
                     double2 gs[P], uh[P];
                     W.ld(V_GSTEP, gs);
                     W.ld(V_UHALF, uh);
-                    const double dist2 = wdiff2<P>(gs, uh);
-                    const double fbe = cost - (0.5 * gamma) * wdot<P>(gr, gr) + (0.5 * dist2) * inv_gamma;
+                    double dist2, gg;
+                    {
+                        double e[P], f[P];
+#pragma unroll
+                        for (int j = 0; j < P; j++) {
+                            double d0 = gs[j].x - uh[j].x, d1 = gs[j].y - uh[j].y;
+                            e[j] = fma(d1, d1, d0 * d0);
+                            f[j] = fma(gr[j].y, gr[j].y, gr[j].x * gr[j].x);
+                        }
+                        hsum2<P>(e, f, dist2, gg);
+                    }
+                    const double fbe = cost - (0.5 * gamma) * gg + (0.5 * dist2) * inv_gamma;
                     rhs_ls = fbe - sigma * (norm_fpr * norm_fpr);
                 }
                 tau = 1.0;
@@ -1060,14 +1245,17 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
 #ifdef NMPC_PROFILE
                 prof[6] = clock64() - tstart;
                 if (prof_out && lane == 0)
-                    for (int i = 0; i < 8; i++) prof_out[i] = prof[i];
+                    for (int i = 0; i < 8; i++) {
+                        prof_out[i] = prof[i];
+                        prof_out[8 + i] = W.pt[i];
+                    }
 #endif
                 st_out.exit_status = status;
                 st_out.outer_iterations = num_outer;
                 st_out.inner_iterations = inner_total;
                 st_out.last_norm_fpr = norm_fpr;
-                st_out.delta_y_norm_over_c = dynp / pn.c;
-                st_out.f2_norm = f2np;
+                st_out.delta_y_norm_over_c = sget(H_DYNP) / pn.c;
+                st_out.f2_norm = sget(H_F2NP);
                 st_out.penalty = pn.c;
                 if (status == NMPC_NOT_FINITE) st_out.cost = CUDART_NAN;
                 st_out.n_cost_evals = n_cost;
@@ -1110,7 +1298,7 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                     u[j].y = u[j].y + hy;
                     x[j] = u[j];
                 }
-                norm_h = sqrt(hsum<P>(e));
+                sput(H_NORMH, sqrt(hsum<P>(e)));
                 mode = MODE_GRAD;
                 phase = PH_INIT_B;
                 break;
@@ -1118,7 +1306,8 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
             case PH_INIT_B: {
                 double2 gr[P], gs[P], uh[P];
                 W.ld(V_GRAD, gr);
-                lip = sqrt(wdiff2<P>(g, gr)) / norm_h;
+                const double lip = sqrt(wdiff2<P>(g, gr)) / sget(H_NORMH);
+                sput(H_LIP, lip);
                 set_gamma(GAMMA_L_COEFF / fmax(lip, MIN_L_ESTIMATE));
                 sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * gamma);
                 grad_step_half(u, gr, gs, uh);
@@ -1198,6 +1387,8 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                     W.st(V_GRAD, g);
 #pragma unroll
                     for (int j = 0; j < P; j++) u[j] = x[j];
+                    fbe_u = lhs;
+                    fbe_valid = true;
                     iteration++;
                     phase = PH_STEP_DONE;
                 }
@@ -1219,8 +1410,10 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                     double d0 = yp[j].x - yl[j].x, d1 = yp[j].y - yl[j].y;
                     e[j] = W.act[j] ? fma(d1, d1, d0 * d0) : 0.0;
                 }
-                dynp = sqrt(hsum<P>(e));
-                f2np = sqrt(pen);
+                const double dynp = sqrt(hsum<P>(e)), f2np = sqrt(pen);
+                const double akkt_tol = sget(H_AKKT);
+                sput(H_DYNP, dynp);
+                sput(H_F2NP, f2np);
                 const bool crit1 = alm_iter > 0 && dynp <= pn.c * cfg.delta_tolerance + DBL_EPS;
                 const bool crit2 = (nf2 == 0) || f2np <= cfg.delta_tolerance + DBL_EPS;
                 const bool crit3 = akkt_tol <= cfg.tolerance + DBL_EPS;
@@ -1229,15 +1422,15 @@ __device__ int solve_problem(Warp<P>& W, double2 (&u)[P], double2 (&yl)[P], nmpc
                     bool stall;
                     if (alm_iter == 0) stall = true;
                     else {
-                        const bool ca = dynp <= cfg.sufficient_decrease_coeff * dyn + DBL_EPS;
-                        const bool cp = f2np <= cfg.sufficient_decrease_coeff * f2n + DBL_EPS;
+                        const bool ca = dynp <= cfg.sufficient_decrease_coeff * sget(H_DYN) + DBL_EPS;
+                        const bool cp = f2np <= cfg.sufficient_decrease_coeff * sget(H_F2N) + DBL_EPS;
                         stall = (nf2 > 0) ? (ca && cp) : ca;
                     }
                     if (!stall) pn = make_pen(pn.c * cfg.penalty_update_factor);
-                    akkt_tol = fmax(akkt_tol * cfg.inner_tolerance_update, cfg.tolerance);
+                    sput(H_AKKT, fmax(akkt_tol * cfg.inner_tolerance_update, cfg.tolerance));
                     alm_iter++;
-                    dyn = dynp;
-                    f2n = f2np;
+                    sput(H_DYN, dynp);
+                    sput(H_F2N, f2np);
 #pragma unroll
                     for (int j = 0; j < P; j++) yl[j] = yp[j];
                     if (num_outer >= cfg.max_outer_iterations) {

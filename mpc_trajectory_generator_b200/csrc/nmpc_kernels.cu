@@ -16,14 +16,17 @@
 #ifndef NMPC_WARPS
 #define NMPC_WARPS 12  // warps (problems in flight) per SM; 32*NMPC_WARPS threads per CTA bounds the registers
 #endif
+// Longer horizons keep 2-3 steps per lane in registers and their arenas are larger (27 KB at N=40, 61 KB at
+// N=80/Nobs=200), so fewer warps fit anyway: cap the CTA accordingly and let ptxas use the registers.
+__host__ __device__ constexpr int warps_cap(int P) { return P == 1 ? NMPC_WARPS : (P == 2 ? 8 : 5); }
 
-template <int P>
-__global__ void __launch_bounds__(32 * NMPC_WARPS, 1) nmpc_solve_kernel(const __grid_constant__ KArgs a) {
+template <int P, int NF>
+__global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const __grid_constant__ KArgs a) {
     const nmpc_config& cfg = a.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Lay L = make_layout(cfg.N_hor, cfg.Nobs, cfg.Ndynobs);
-    const int N = cfg.N_hor;
-    Warp<P> W(cfg, L, warp, lane);
+    const int N = NF ? NF : cfg.N_hor;
+    Warp<P, NF> W(cfg, L, warp, lane);
     for (;;) {
         int b = 0;
         if (lane == 0) b = (int)atomicAdd(a.counter, 1u);
@@ -42,9 +45,9 @@ __global__ void __launch_bounds__(32 * NMPC_WARPS, 1) nmpc_solve_kernel(const __
         nmpc_stats st;
         st.cost = 0.0;
 #ifdef NMPC_PROFILE
-        const int status = solve_problem<P>(W, u, yl, st, a.dbg ? a.dbg + (size_t)b * 8 : nullptr);
+        const int status = solve_problem<P, NF>(W, u, yl, st, a.dbg ? a.dbg + (size_t)b * 16 : nullptr);
 #else
-        const int status = solve_problem<P>(W, u, yl, st);
+        const int status = solve_problem<P, NF>(W, u, yl, st);
 #endif
 #pragma unroll
         for (int j = 0; j < P; j++) {
@@ -65,14 +68,14 @@ __global__ void __launch_bounds__(32 * NMPC_WARPS, 1) nmpc_solve_kernel(const __
 }
 
 // parity hook: psi, grad, F1, F2 for B (p, u, c, y) tuples
-template <int P>
-__global__ void __launch_bounds__(32 * NMPC_WARPS, 1) nmpc_eval_kernel(const __grid_constant__ KArgs a) {
+template <int P, int NF>
+__global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_eval_kernel(const __grid_constant__ KArgs a) {
     const nmpc_config& cfg = a.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Lay L = make_layout(cfg.N_hor, cfg.Nobs, cfg.Ndynobs);
-    const int N = cfg.N_hor, nf2 = cfg.Nobs + cfg.Ndynobs;
+    const int N = NF ? NF : cfg.N_hor, nf2 = cfg.Nobs + cfg.Ndynobs;
     const int wpb = blockDim.x >> 5;
-    Warp<P> W(cfg, L, warp, lane);
+    Warp<P, NF> W(cfg, L, warp, lane);
     for (int b = blockIdx.x * wpb + warp; b < a.B; b += gridDim.x * wpb) {
         W.stage(a.P + (size_t)b * a.np);
         double2 u[P], yl[P], g[P];
@@ -179,18 +182,30 @@ const char* nmpc_exit_status_name(int32_t s) {
 
 const char* nmpc_last_error(nmpc_handle* h) { return h ? h->err : "null handle"; }
 
-static const void* solve_kernel_for(int P) {
-    switch (P) {
-        case 1: return (const void*)nmpc_solve_kernel<1>;
-        case 2: return (const void*)nmpc_solve_kernel<2>;
-        default: return (const void*)nmpc_solve_kernel<3>;
+// Optional compile-time-N instantiation (fully unrolled cross-track loop with a tree arg-min).  Measured on
+// B200 (round 1, tools/variants.py): a lone warp's evaluation gets 15 % faster, but the larger hot loop costs
+// more in instruction fetch than it saves (config 2: 45.6k vs 48.6k solves/s), so it is off by default.
+#ifndef NMPC_FIXED_N
+#define NMPC_FIXED_N 0
+#endif
+static const void* solve_kernel_for(int N) {
+#if NMPC_FIXED_N > 0
+    if (N == NMPC_FIXED_N) return (const void*)nmpc_solve_kernel<(NMPC_FIXED_N + 31) / 32, NMPC_FIXED_N>;
+#endif
+    switch ((N + 31) / 32) {
+        case 1: return (const void*)nmpc_solve_kernel<1, 0>;
+        case 2: return (const void*)nmpc_solve_kernel<2, 0>;
+        default: return (const void*)nmpc_solve_kernel<3, 0>;
     }
 }
-static const void* eval_kernel_for(int P) {
-    switch (P) {
-        case 1: return (const void*)nmpc_eval_kernel<1>;
-        case 2: return (const void*)nmpc_eval_kernel<2>;
-        default: return (const void*)nmpc_eval_kernel<3>;
+static const void* eval_kernel_for(int N) {
+#if NMPC_FIXED_N > 0
+    if (N == NMPC_FIXED_N) return (const void*)nmpc_eval_kernel<(NMPC_FIXED_N + 31) / 32, NMPC_FIXED_N>;
+#endif
+    switch ((N + 31) / 32) {
+        case 1: return (const void*)nmpc_eval_kernel<1, 0>;
+        case 2: return (const void*)nmpc_eval_kernel<2, 0>;
+        default: return (const void*)nmpc_eval_kernel<3, 0>;
     }
 }
 
@@ -229,12 +244,12 @@ int nmpc_create(const nmpc_config* cfg, int device, nmpc_handle** out) {
         delete h;
         return NMPC_ERR_INVALID;  // problem too large for one warp's arena
     }
-    if (w > NMPC_WARPS) w = NMPC_WARPS;
+    if (w > warps_cap(h->P)) w = warps_cap(h->P);
     h->warps_per_cta = w;
     h->smem_bytes = per_warp * w;
-    e = cudaFuncSetAttribute(solve_kernel_for(h->P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    e = cudaFuncSetAttribute(solve_kernel_for(h->cfg.N_hor), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(eval_kernel_for(h->P), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+        e = cudaFuncSetAttribute(eval_kernel_for(h->cfg.N_hor), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&h->counter, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&h->call_u, 2 * cfg->N_hor * sizeof(double));
@@ -300,7 +315,7 @@ static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU,
     if (grid > ctas_needed) grid = ctas_needed;
     if (grid < 1) grid = 1;
     void* args[] = {&a};
-    CUDA_TRY(h, cudaLaunchKernel(solve_kernel_for(h->P), dim3(grid), dim3(32 * h->warps_per_cta), args, h->smem_bytes, s));
+    CUDA_TRY(h, cudaLaunchKernel(solve_kernel_for(h->cfg.N_hor), dim3(grid), dim3(32 * h->warps_per_cta), args, h->smem_bytes, s));
     h->launches++;
     return NMPC_OK;
 }
@@ -424,7 +439,7 @@ int nmpc_eval_batch(nmpc_handle* h, int32_t B, const double* P, const double* U,
         int grid = (B + h->warps_per_cta - 1) / h->warps_per_cta;
         if (grid > 8 * h->sm_count) grid = 8 * h->sm_count;
         void* args[] = {&a};
-        e = cudaLaunchKernel(eval_kernel_for(h->P), dim3(grid), dim3(32 * h->warps_per_cta), args, h->smem_bytes, s);
+        e = cudaLaunchKernel(eval_kernel_for(h->cfg.N_hor), dim3(grid), dim3(32 * h->warps_per_cta), args, h->smem_bytes, s);
         h->launches++;
     }
     if (psi) TRY_(cudaMemcpyAsync(psi, dpsi, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));

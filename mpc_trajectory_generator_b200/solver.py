@@ -89,9 +89,11 @@ def load_library(build=True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if build and _build.is_stale() and _build.find_nvcc():
-        _build.build_library()
+    path = os.environ.get("NMPC_B200_LIB")   # tools/: a tuning/profiling build of the same sources
+    if path is None:
+        path = _build.LIB
+        if build and _build.is_stale() and _build.find_nvcc():
+            _build.build_library()
     if not os.path.exists(path):
         raise NmpcError(f"{path} not found and nvcc unavailable: the CUDA solver library is required "
                         "(there is no CPU fallback)")
