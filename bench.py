@@ -117,11 +117,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(name, batch, seed, N=20):
-    """-> (P, U0, Y0, host_cfg, description)"""
+def make_workload(name, batch, seed, N=20, device=None):
+    """-> (P, U0, Y0, host_cfg, description).  config3/config4 are recorded closed-loop steps: on the GPU arm the
+    fleet API records them on `device`; on the CPU arm the host loop + oracle records the same steps."""
     from mpc_trajectory_generator_b200 import workloads
     from mpc_trajectory_generator_b200.host import assembly
     hc = assembly.HostConfig.default(N_hor=N)
+    if name in ("config3", "config4"):
+        if name == "config4":
+            hc = assembly.HostConfig.smooth_velocity(N_hor=40)
+        robots = max(1, int(round(batch ** 0.5)))
+        steps = max(1, batch // robots)
+        if device is not None:
+            import mpc_trajectory_generator_b200 as pkg
+            s = pkg.NmpcSolver(workloads.solver_config_for(hc), device=device)
+            rec = workloads.closed_loop_batch_device(s, hc, complexity=11, robots=robots, steps=steps, seed=seed + 1)
+            s.close()
+        else:
+            from oracle import oracle_c
+            ocfg = oracle_c.default_config(**{k: getattr(workloads.solver_config_for(hc), k) for k in
+                                              ("N_hor", "Nobs", "Ndynobs", "ang_vel_max", "ang_acc_max")})
+            rec = workloads.closed_loop_batch(
+                hc, lambda P, U0, Y0: oracle_c.solve_batch(ocfg, P, U0, Y0, nthreads=host_threads())[:3],
+                complexity=11, robots=robots, steps=steps, seed=seed + 1, sincos=oracle_c.sincos)
+        desc = (f"configs[{2 if name == 'config3' else 3}]: {rec['P'].shape[0]} recorded receding-horizon steps "
+                f"({robots} robots x <= {steps} steps, map complexity=11, N={hc.N_hor}), warm start = previous solution")
+        return rec["P"], rec["U0"], rec["Y0"], hc, desc
     if name == "config2":
         P, _ = workloads.first_step_batch(hc, complexity=3, B=batch, seed=seed)
         desc = f"configs[1]: batch={batch} random start/goal pairs, map complexity=3, N={N}, first step, cold start"
@@ -141,15 +162,19 @@ def run_reference(args, rank, world):
     from oracle import oracle_c
     oracle_c.build()
     P, U0, Y0, hc, desc = make_workload(args.workload, args.batch, args.seed)
-    cfg = oracle_c.default_config(N_hor=hc.N_hor, Nobs=hc.Nobs, Ndynobs=hc.Ndynobs)
+    cfg = oracle_c.default_config(N_hor=hc.N_hor, Nobs=hc.Nobs, Ndynobs=hc.Ndynobs, ang_vel_max=hc.ang_vel_max,
+                                  ang_acc_max=hc.ang_acc_max)
     threads = host_threads()   # torchrun pins OMP_NUM_THREADS=1; the CPU arm uses every host core it may run on
     sample = min(args.ref_sample, P.shape[0])
     Ps = P[:sample]
+    U0s = None if U0 is None else U0[:sample]
+    Y0s = None if Y0 is None else Y0[:sample]
     for _ in range(args.warmup):
-        oracle_c.solve_batch(cfg, Ps[:min(32, sample)], nthreads=threads)
+        oracle_c.solve_batch(cfg, Ps[:min(32, sample)], None if U0s is None else U0s[:32],
+                             None if Y0s is None else Y0s[:32], nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, _, st, _ = oracle_c.solve_batch(cfg, Ps, nthreads=threads)
+        _, _, st, _ = oracle_c.solve_batch(cfg, Ps, U0s, Y0s, nthreads=threads)
     dt = time.perf_counter() - t0
     val = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -202,7 +227,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # rank r generates its own shard (weak scaling: per-GPU batch fixed)
-    P, U0, Y0, hc, desc = make_workload(args.workload, args.batch, args.seed + rank)
+    P, U0, Y0, hc, desc = make_workload(args.workload, args.batch, args.seed + rank, device=local_rank)
     B = P.shape[0]
     N, Nobs, Nd = hc.N_hor, hc.Nobs, hc.Ndynobs
     cfg = workloads.solver_config_for(hc)
@@ -335,7 +360,8 @@ def main():
         if not args.no_cpu_baseline and world >= 1:
             from oracle import oracle_c
             oracle_c.build()
-            ocfg = oracle_c.default_config(N_hor=N, Nobs=Nobs, Ndynobs=Nd)
+            ocfg = oracle_c.default_config(N_hor=N, Nobs=Nobs, Ndynobs=Nd, ang_vel_max=hc.ang_vel_max,
+                                           ang_acc_max=hc.ang_acc_max)
             threads = host_threads()   # torchrun pins OMP_NUM_THREADS=1; the CPU arm uses every host core it may run on
             t0 = time.perf_counter()
             oracle_c.solve_batch(ocfg, P[:64], None if U0 is None else U0[:64], None if Y0 is None else Y0[:64],

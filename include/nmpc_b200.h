@@ -160,6 +160,66 @@ int nmpc_solve_batch_device(nmpc_handle* h, int32_t B, const double* dP, double*
 int nmpc_eval_batch(nmpc_handle* h, int32_t B, const double* P, const double* U, const double* c,
                     const double* Y, double* psi, double* grad, double* F1, double* F2);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fleet stepping: the receding-horizon loop of PathGenerator.run
+ * (src/path_generator.py:290-403) for B robots at once, entirely on the device.  One step =
+ *   assemble  the per-step parameter vector of every live robot (src/path_generator.py:293-382:
+ *             closest-vertex window, reference window + goal padding, vel_ref brake ramp,
+ *             dynamic-obstacle ring; helpers src/visibility/visibility.py:111-124,141-148,199-216),
+ *   solve     the batch with the persisted, un-shifted warm start (u, y) of each robot — what the
+ *             reference's solver process keeps between mng.call()s (src/mpc/mpc_generator.py:206),
+ *   advance   apply the first control, integrate the plant (src/mpc/mpc_generator.py:223-235) and
+ *             run the termination test (src/path_generator.py:397).
+ * n steps are enqueued back to back on the handle's stream without a host round trip.
+ * Restrictions (documented deviations): num_steps_taken = 1 (configs/default.yaml:17); a map has either
+ * no dynamic obstacles (phantom unit discs, src/path_generator.py:274-280) or exactly Ndynobs of them.
+ */
+typedef struct nmpc_fleet nmpc_fleet;
+
+typedef struct nmpc_fleet_config {
+    int32_t n_robots;
+    int32_t max_ref;   /* capacity (points) of one robot's sampled reference, rough_ref() output */
+    int32_t max_vert;  /* capacity of one robot's corner-vertex list (find_original_vertices)    */
+    int32_t n_brake;   /* entries of the brake profile (get_brake_vel_ref)                       */
+    int32_t n_sched;   /* rows of the dynamic-obstacle schedule; 0 = map without dynamic obstacles */
+    int32_t log_steps; /* per-robot trajectory log capacity in steps (0 = no log)               */
+    int32_t reserved0, reserved1;
+    double base_speed;    /* lin_vel_max * throttle_ratio (src/path_generator.py:352)            */
+    double circle_radius; /* vehicle_width/2 + vehicle_margin (src/path_generator.py:301)        */
+    double goal_tol;      /* 0.05  (src/path_generator.py:397)                                   */
+    double stop_tol;      /* 0.005 (src/path_generator.py:397)                                   */
+    double weights[10];   /* z0[10:20], order of src/path_generator.py:226-227                   */
+} nmpc_fleet_config;
+
+int nmpc_fleet_create(nmpc_handle* h, const nmpc_fleet_config* fc, nmpc_fleet** out);
+int nmpc_fleet_destroy(nmpc_fleet* f);
+
+/* Upload the per-robot plans (HOST buffers) and reset every robot to step 0 (state = start, last input 0,
+ * reference index 0, warm start zeros):
+ *   n_ref[B], ref[B, max_ref, 3]   (x, y, theta) samples of rough_ref (src/mpc/mpc_generator.py:17-57)
+ *   n_vert[B], vert[B, max_vert, 2] original vertices of the A* corners (src/visibility/visibility.py:126-139)
+ *   start[B, 3], goal[B, 3]
+ *   brake_vel[n_brake], brake_dist[n_brake]     (src/path_generator.py:439-477)
+ *   sched_init[N, Ndynobs, 5], sched[n_sched, Ndynobs, 5]  (x, y, rx, ry, angle) of every dynamic obstacle:
+ *       sched_init[m] = entry m of the t=0 fill (np.linspace(0, N*ts, N) times, src/visibility/visibility.py:204),
+ *       sched[m]      = the entry appended for time m*ts (m >= N); both NULL when n_sched == 0. */
+int nmpc_fleet_load(nmpc_fleet* f, const int32_t* n_ref, const double* ref, const int32_t* n_vert,
+                    const double* vert, const double* start, const double* goal, const double* brake_vel,
+                    const double* brake_dist, const double* sched_init, const double* sched);
+
+/* run n_steps receding-horizon steps for every robot that has not terminated; synchronous */
+int nmpc_fleet_step(nmpc_fleet* f, int32_t n_steps);
+
+/* Read-back (HOST buffers, any pointer nullable):
+ *   state[B,3], last_u[B,2], t[B] steps taken, idx[B] reference index, done[B] terminal flag,
+ *   status[B] exit status of the last solve */
+int nmpc_fleet_state(nmpc_fleet* f, double* state, double* last_u, int32_t* t, int32_t* idx, int32_t* done,
+                     int32_t* status);
+/* parameter rows assembled for the LAST step, P[B, np]; last solution U[B, 2N] and multipliers Y[B, 2N] */
+int nmpc_fleet_last(nmpc_fleet* f, double* P, double* U, double* Y);
+/* trajectory log: log[B, log_steps, 5] = (x, y, theta after the step, v, omega applied); n_logged[B] */
+int nmpc_fleet_log(nmpc_fleet* f, double* log, int32_t* n_logged);
+
 /* number of kernel launches issued through this handle since creation */
 int64_t nmpc_launch_count(nmpc_handle* h);
 

@@ -92,6 +92,7 @@ struct KArgs {
     int32_t* status;
     nmpc_stats* stats;
     unsigned int* counter;
+    const int32_t* skip;  // nullable: rows with skip[b] != 0 are left untouched (fleet: robots that have terminated)
     // eval kernel only
     const double* cvec;
     double *psi, *grad, *F1, *F2;
@@ -345,6 +346,40 @@ __device__ __forceinline__ void suffix_scan2(const double (&xa)[P], const double
             cb = __shfl_sync(FULL, gb, 0);
         }
     }
+}
+// suffix_scan2 with an independent xor-butterfly sum riding along in the same instruction stream: the stages of
+// the two reductions interleave, so the cost sum of a gradient evaluation costs no extra latency.
+// Each of the three results is bit-identical to suffix_scan2 / hsum.
+template <int P>
+__device__ __forceinline__ void suffix_scan2_hsum(const double (&xa)[P], const double (&xb)[P], double (&sa)[P],
+                                                  double (&sb)[P], const double (&e)[P], double& esum, int lane) {
+    double acc = e[0];
+#pragma unroll
+    for (int j = 1; j < P; j++) acc = acc + e[j];
+    double ca = 0.0, cb = 0.0;
+#pragma unroll
+    for (int j = P - 1; j >= 0; j--) {
+        double la = xa[j], lb = xb[j];
+#pragma unroll
+        for (int st = 0; st < 5; st++) {
+            const int off = 1 << st;
+            double ya = __shfl_down_sync(FULL, la, off);
+            double yb = __shfl_down_sync(FULL, lb, off);
+            double yc = 0.0;
+            if (j == P - 1) yc = __shfl_xor_sync(FULL, acc, 16 >> st);
+            add_if(la, ya, lane + off < 32);
+            add_if(lb, yb, lane + off < 32);
+            if (j == P - 1) acc = acc + yc;
+        }
+        double ga = (j == P - 1) ? la : ca + la, gb = (j == P - 1) ? lb : cb + lb;
+        sa[j] = ga;
+        sb[j] = gb;
+        if (j > 0) {
+            ca = __shfl_sync(FULL, ga, 0);
+            cb = __shfl_sync(FULL, gb, 0);
+        }
+    }
+    esum = acc;
 }
 template <int P>
 __device__ __forceinline__ double wdot(const double2 (&a)[P], const double2 (&b)[P]) {
@@ -824,9 +859,11 @@ struct Warp {
             }
         const double eXN = XN - xref, eYN = YN - yref, eTN = TN - thref;
         const double term = fma(w_qN, fma(eXN, eXN, eYN * eYN), w_qthN * (eTN * eTN));
-        const double psi = fma(pn.hc, pen, hsum<P>(cl) + term);
-        PROF_MARK(4);
-        if (!GRAD) return psi;
+        if (!GRAD) {
+            const double psi0 = fma(pn.hc, pen, hsum<P>(cl) + term);
+            PROF_MARK(4);
+            return psi0;
+        }
 
         // backward sweep
         double mth[P];
@@ -838,8 +875,10 @@ struct Warp {
             gY[j] = act[j] ? fma(2.0 * qq, Y[j] - yref, gY[j]) : 0.0;
             mth[j] = act[j] ? (2.0 * qt) * (TH[j] - thref) : 0.0;
         }
-        double LX[P], LY[P];
-        suffix_scan2<P>(gX, gY, LX, LY, lane);
+        double LX[P], LY[P], csum;
+        suffix_scan2_hsum<P>(gX, gY, LX, LY, cl, csum, lane);  // position adjoints + the cost sum
+        const double psi = fma(pn.hc, pen, csum + term);
+        PROF_MARK(4);
         double nn[P], rr[P], TT[P];
 #pragma unroll
         for (int j = 0; j < P; j++) nn[j] = act[j] ? (ts * uv[j].x) * fma(cs[j], LY[j], -(sn[j] * LX[j])) : 0.0;

@@ -1,0 +1,228 @@
+// nmpc_fleet.cuh — device side of the fleet stepping API (include/nmpc_b200.h, "Fleet stepping").
+//
+// The reference assembles one robot's parameter vector per receding-horizon step with Python list
+// slicing (src/path_generator.py:293-382) and integrates the plant in MpcModule.run
+// (src/mpc/mpc_generator.py:223-235).  Here both run on the device for B robots: one warp per robot
+// assembles its row of P straight into HBM (coalesced stores, lanes stride the row), the solve kernel
+// picks the rows up from there, and one thread per robot applies the first control and advances the plant.
+// The arithmetic that decides anything (arg-min distances, brake-ramp filter, termination test, Euler
+// step) is written operation for operation like the reference's Python floats; the plant's sin/cos is the
+// solver's own nm_sincos (<= 2 ulp from libm), see tests/test_fleet.py for what that means for parity.
+#pragma once
+#include "nmpc_device.cuh"
+
+struct FleetArgs {
+    nmpc_config cfg;
+    nmpc_fleet_config fc;
+    int np;
+    // plans (read only)
+    const int32_t* n_ref;
+    const double* ref;      // [B, max_ref, 3]
+    const int32_t* n_vert;
+    const double* vert;     // [B, max_vert, 2]
+    const double* goal;     // [B, 3]
+    const double* brake_vel;
+    const double* brake_dist;
+    const double* sched_init;  // [N, Nd, 5]
+    const double* sched;       // [n_sched, Nd, 5]
+    // per-robot run state
+    double* state;    // [B, 3]
+    double* last_u;   // [B, 2]
+    int32_t* t;       // steps taken
+    int32_t* idx;     // reference index
+    int32_t* done;    // 0 live, 1 terminal (goal reached and stopped), 2 solver failure (NotFinite)
+    // solver I/O
+    double* P;        // [B, np]
+    const double* U;  // [B, 2N]
+    const int32_t* status;
+    // log
+    double* log;      // [B, log_steps, 5]
+    int32_t* n_logged;
+};
+
+// (distance^2, index) arg-min over the warp; ties go to the lower index (np.argmin returns the first minimum)
+__device__ __forceinline__ void warp_argmin(double& d, int& i) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        const double od = __shfl_xor_sync(FULL, d, off);
+        const int oi = __shfl_xor_sync(FULL, i, off);
+        if (od < d || (od == d && oi < i)) {
+            d = od;
+            i = oi;
+        }
+    }
+}
+
+// squared 2-norm the way the reference measures closeness (np.linalg.norm -> sqrt(x.x), src/visibility/visibility.py:111-124);
+// sqrt is monotone, so the arg-min over d^2 is the arg-min over d except for distances that differ in the last ulp.
+__device__ __forceinline__ double dist2(double ax, double ay, double bx, double by) {
+    const double dx = ax - bx, dy = ay - by;
+    return dx * dx + dy * dy;
+}
+
+// One warp per robot: src/path_generator.py:293-382 for the robot's current state.
+__global__ void __launch_bounds__(256) fleet_assemble_kernel(const __grid_constant__ FleetArgs f) {
+    const int lane = threadIdx.x & 31;
+    const int b = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    if (b >= f.fc.n_robots) return;
+    if (f.done[b]) return;
+    const int N = f.cfg.N_hor, Nobs = f.cfg.Nobs, Nd = f.cfg.Ndynobs;
+    double* __restrict__ p = f.P + (size_t)b * f.np;
+    const double x = f.state[3 * b], y = f.state[3 * b + 1], th = f.state[3 * b + 2];
+    const double lv = f.last_u[2 * b], lw = f.last_u[2 * b + 1];
+    const double* __restrict__ goal = f.goal + 3 * (size_t)b;
+    const double gx = goal[0], gy = goal[1], gth = goal[2];
+    const int t = f.t[b];
+
+    // ---- reference index: closest sample inside [idx-1, idx+5) (src/path_generator.py:330-333)
+    const int n = f.n_ref[b];
+    const double* __restrict__ R = f.ref + (size_t)b * f.fc.max_ref * 3;
+    int idx = f.idx[b];
+    {
+        const int lb = max(0, idx - 1), ub = min(n, idx + 5);
+        double d = CUDART_INF;
+        int i = 0x7fffffff;
+        if (lb + lane < ub) {
+            d = dist2(x, y, R[3 * (lb + lane)], R[3 * (lb + lane) + 1]);
+            i = lane;
+        }
+        warp_argmin(d, i);
+        idx = lb + i;
+        if (lane == 0) f.idx[b] = idx;
+    }
+
+    // ---- header: state, last input (twice), horizon-end reference, weights (src/path_generator.py:378-379)
+    if (lane < 3) p[lane] = (lane == 0) ? x : ((lane == 1) ? y : th);
+    if (lane == 3 || lane == 8) p[lane] = lv;
+    if (lane == 4 || lane == 9) p[lane] = lw;
+    if (lane >= 5 && lane < 8) {
+        const int c = lane - 5;
+        p[lane] = (idx + N >= n) ? goal[c] : R[3 * (idx + N) + c];  // x_finish (:336-344)
+    }
+    if (lane >= 10 && lane < 20) p[lane] = f.fc.weights[lane - 10];
+
+    // ---- vel_ref with the brake ramp (src/path_generator.py:352-367)
+    {
+        double* __restrict__ vr = p + NMPC_NZ;
+        const double base = f.fc.base_speed;
+        const int nbk = f.fc.n_brake;
+        if ((double)(idx + N) >= (double)n - f.brake_dist[0] / base) {
+            const int nb = min(n - idx - 1, N);
+            if (nb == 0) {
+                // only brake entries whose stopping distance fits the remaining distance, order kept
+                const double ddx = x - gx, ddy = y - gy;
+                const double d = sqrt(ddx * ddx + ddy * ddy);
+                int out = 0;
+                for (int k0 = 0; k0 < nbk; k0 += 32) {
+                    const int k = k0 + lane;
+                    const bool keep = (k < nbk) && (f.brake_dist[k] <= d);
+                    const unsigned m = __ballot_sync(FULL, keep);
+                    const int pos = out + __popc(m & ((1u << lane) - 1u));
+                    if (keep && pos < N) vr[pos] = f.brake_vel[k];
+                    out += __popc(m);
+                }
+                for (int j = min(out, N) + lane; j < N; j += 32) vr[j] = 0.0;
+            } else {
+                const int nramp = min(nbk, N - nb);
+                for (int j = lane; j < N; j += 32)
+                    vr[j] = (j < nb) ? base : ((j < nb + nramp) ? f.brake_vel[j - nb] : 0.0);
+            }
+        } else {
+            for (int j = lane; j < N; j += 32) vr[j] = base;
+        }
+    }
+
+    // ---- static circles: the corner vertices closest to the robot (src/path_generator.py:299-304,
+    //      find_closest_vertices with its slice quirk vert[idx:Nobs], src/visibility/visibility.py:141-148)
+    {
+        double* __restrict__ pc = p + NMPC_NZ + N;
+        const int nv = f.n_vert[b];
+        const double* __restrict__ V = f.vert + (size_t)b * f.fc.max_vert * 2;
+        int first = 0, cnt = nv;
+        if (nv > Nobs) {
+            double d = CUDART_INF;
+            int i = 0x7fffffff;
+            for (int k = lane; k < nv; k += 32) {
+                const double dk = dist2(x, y, V[2 * k], V[2 * k + 1]);
+                if (dk < d) {
+                    d = dk;
+                    i = k;
+                }
+            }
+            warp_argmin(d, i);
+            first = i;
+            cnt = max(0, min(nv, Nobs) - first);
+        }
+        for (int k = lane; k < Nobs; k += 32) {
+            const bool on = k < cnt;
+            pc[3 * k] = on ? V[2 * (first + k)] : 0.0;
+            pc[3 * k + 1] = on ? V[2 * (first + k) + 1] : 0.0;
+            pc[3 * k + 2] = on ? f.fc.circle_radius : 0.0;
+        }
+    }
+
+    // ---- dynamic ellipses: slot j of the ring at step t holds schedule entry m = t + j
+    //      (the t=0 fill for m < N, the per-step appended entries after; src/path_generator.py:306-326)
+    {
+        double* __restrict__ pe = p + NMPC_NZ + N + 3 * Nobs;
+        const int ne = Nd * N;
+        for (int i = lane; i < ne; i += 32) {
+            const int k = i / N, j = i - k * N;
+            double* __restrict__ e = pe + 5 * (size_t)i;  // obstacle-major, then time
+            if (f.fc.n_sched == 0) {
+                e[0] = 0.0; e[1] = 0.0; e[2] = 1.0; e[3] = 1.0; e[4] = 0.0;  // phantom unit disc (:274-280)
+            } else {
+                const int m = t + j;
+                const int mm = min(m, f.fc.n_sched - 1);
+                const double* __restrict__ s = (m < N) ? f.sched_init + 5 * ((size_t)m * Nd + k) : f.sched + 5 * ((size_t)mm * Nd + k);
+#pragma unroll
+                for (int c = 0; c < 5; c++) e[c] = s[c];
+            }
+        }
+    }
+
+    // ---- reference window, padded with the goal pose past the end of the path (src/path_generator.py:336-350,369-373)
+    {
+        double* __restrict__ pr = p + NMPC_NZ + N + 3 * Nobs + 5 * Nd * N;
+        for (int i = lane; i < 3 * N; i += 32) {
+            const int j = i / 3, c = i - 3 * j;
+            pr[i] = (idx + j < n) ? R[3 * (idx + j) + c] : goal[c];
+        }
+    }
+}
+
+// One thread per robot: MpcModule.run's apply + plant step (src/mpc/mpc_generator.py:223-235) and the
+// termination test of the loop (src/path_generator.py:397).
+__global__ void __launch_bounds__(256) fleet_advance_kernel(const __grid_constant__ FleetArgs f) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= f.fc.n_robots) return;
+    if (f.done[b]) return;
+    if (f.status[b] == NMPC_NOT_FINITE) {  // reference: RuntimeError("MPC Solver error") ends the run
+        f.done[b] = 2;
+        return;
+    }
+    const int N2 = 2 * f.cfg.N_hor;
+    const double v = f.U[(size_t)b * N2], w = f.U[(size_t)b * N2 + 1];
+    double x = f.state[3 * b], y = f.state[3 * b + 1], th = f.state[3 * b + 2];
+    double s, c;
+    nm_sincos(th, s, c);
+    const double ts = f.cfg.ts;
+    x = x + ts * (v * c);
+    y = y + ts * (v * s);
+    th = th + ts * w;
+    f.state[3 * b] = x;
+    f.state[3 * b + 1] = y;
+    f.state[3 * b + 2] = th;
+    f.last_u[2 * b] = v;
+    f.last_u[2 * b + 1] = w;
+    const int t = f.t[b];
+    f.t[b] = t + 1;
+    if (f.log && t < f.fc.log_steps) {
+        double* l = f.log + ((size_t)b * f.fc.log_steps + t) * 5;
+        l[0] = x; l[1] = y; l[2] = th; l[3] = v; l[4] = w;
+        f.n_logged[b] = t + 1;
+    }
+    const double* goal = f.goal + 3 * (size_t)b;
+    // np.allclose(states[-3:-1], end[0:2], atol=0.05, rtol=0) and abs(system_input[-2]) < 0.005
+    if (fabs(x - goal[0]) <= f.fc.goal_tol && fabs(y - goal[1]) <= f.fc.goal_tol && fabs(v) < f.fc.stop_tol) f.done[b] = 1;
+}

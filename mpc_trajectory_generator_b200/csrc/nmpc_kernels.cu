@@ -12,6 +12,7 @@
 #include <new>
 
 #include "nmpc_device.cuh"
+#include "nmpc_fleet.cuh"
 
 #ifndef NMPC_WARPS
 #define NMPC_WARPS 12  // warps (problems in flight) per SM; 32*NMPC_WARPS threads per CTA bounds the registers
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const 
         if (lane == 0) b = (int)atomicAdd(a.counter, 1u);
         b = __shfl_sync(FULL, b, 0);
         if (b >= a.B) break;
+        if (a.skip && a.skip[b]) continue;
         W.stage(a.P + (size_t)b * a.np);
         double2 u[P], yl[P];
         const double* U0 = a.U + (size_t)b * 2 * N;
@@ -293,7 +295,7 @@ int nmpc_ping(nmpc_handle* h) {
 }
 
 static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU, double* dY, int32_t* dstatus,
-                        nmpc_stats* dstats, cudaStream_t s) {
+                        nmpc_stats* dstats, cudaStream_t s, const int32_t* dskip = nullptr) {
     KArgs a;
     memset(&a, 0, sizeof(a));
     a.cfg = h->cfg;
@@ -305,6 +307,7 @@ static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU,
     a.status = dstatus;
     a.stats = dstats;
     a.counter = h->counter;
+    a.skip = dskip;
 #ifdef NMPC_PROFILE
     a.dbg = g_dbg;
 #endif
@@ -452,6 +455,206 @@ int nmpc_eval_batch(nmpc_handle* h, int32_t B, const double* P, const double* U,
     cudaFree(dP); cudaFree(dU); cudaFree(dY); cudaFree(dc); cudaFree(dpsi); cudaFree(dgrad); cudaFree(dF1); cudaFree(dF2);
     return rc;
 }
+
+
+// ---------------------------------------------------------------------------------
+// fleet stepping (include/nmpc_b200.h "Fleet stepping"; device code in nmpc_fleet.cuh)
+}  // extern "C"
+struct nmpc_fleet {
+    nmpc_handle* h;
+    nmpc_fleet_config fc;
+    FleetArgs a;  // device pointers
+    nmpc_stats* dstats;
+    double *dU, *dY;
+    int32_t* dstatus;
+    bool loaded;
+};
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)); }
+extern "C" {
+
+int nmpc_fleet_create(nmpc_handle* h, const nmpc_fleet_config* fc, nmpc_fleet** out) {
+    if (!h || !fc || !out) return NMPC_ERR_INVALID;
+    *out = nullptr;
+    if (fc->n_robots < 1 || fc->max_ref < 1 || fc->max_vert < 0 || fc->n_brake < 1 || fc->n_sched < 0 || fc->log_steps < 0 ||
+        !(fc->base_speed > 0.0))
+        return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_create: bad fleet config%s", "");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    nmpc_fleet* f = new (std::nothrow) nmpc_fleet();
+    if (!f) return NMPC_ERR_NOMEM;
+    memset(f, 0, sizeof(*f));
+    f->h = h;
+    f->fc = *fc;
+    FleetArgs& a = f->a;
+    a.cfg = h->cfg;
+    a.fc = *fc;
+    a.np = h->np;
+    const size_t B = fc->n_robots, N = h->cfg.N_hor, Nd = h->cfg.Ndynobs;
+    cudaError_t e = cudaSuccess;
+#define TRY_(call) if (e == cudaSuccess) e = (call)
+    TRY_(dalloc((int32_t**)&a.n_ref, B));
+    TRY_(dalloc((double**)&a.ref, B * fc->max_ref * 3));
+    TRY_(dalloc((int32_t**)&a.n_vert, B));
+    TRY_(dalloc((double**)&a.vert, B * fc->max_vert * 2));
+    TRY_(dalloc((double**)&a.goal, B * 3));
+    TRY_(dalloc((double**)&a.brake_vel, (size_t)fc->n_brake));
+    TRY_(dalloc((double**)&a.brake_dist, (size_t)fc->n_brake));
+    TRY_(dalloc((double**)&a.sched_init, N * Nd * 5));
+    TRY_(dalloc((double**)&a.sched, (size_t)fc->n_sched * Nd * 5));
+    TRY_(dalloc(&a.state, B * 3));
+    TRY_(dalloc(&a.last_u, B * 2));
+    TRY_(dalloc(&a.t, B));
+    TRY_(dalloc(&a.idx, B));
+    TRY_(dalloc(&a.done, B));
+    TRY_(dalloc(&a.P, B * h->np));
+    TRY_(dalloc(&f->dU, B * 2 * N));
+    TRY_(dalloc(&f->dY, B * 2 * N));
+    TRY_(dalloc(&f->dstatus, B));
+    TRY_(dalloc(&f->dstats, B));
+    if (fc->log_steps > 0) {
+        TRY_(dalloc(&a.log, B * fc->log_steps * 5));
+        TRY_(dalloc(&a.n_logged, B));
+    }
+#undef TRY_
+    a.U = f->dU;
+    a.status = f->dstatus;
+    if (e != cudaSuccess) {
+        set_err(h, NMPC_ERR_CUDA, "nmpc_fleet_create: %s", cudaGetErrorString(e));
+        nmpc_fleet_destroy(f);
+        return NMPC_ERR_CUDA;
+    }
+    *out = f;
+    return NMPC_OK;
+}
+
+int nmpc_fleet_destroy(nmpc_fleet* f) {
+    if (!f) return NMPC_OK;
+    cudaSetDevice(f->h->device);
+    cudaStreamSynchronize(f->h->stream);
+    FleetArgs& a = f->a;
+    cudaFree((void*)a.n_ref); cudaFree((void*)a.ref); cudaFree((void*)a.n_vert); cudaFree((void*)a.vert);
+    cudaFree((void*)a.goal); cudaFree((void*)a.brake_vel); cudaFree((void*)a.brake_dist);
+    cudaFree((void*)a.sched_init); cudaFree((void*)a.sched);
+    cudaFree(a.state); cudaFree(a.last_u); cudaFree(a.t); cudaFree(a.idx); cudaFree(a.done); cudaFree(a.P);
+    cudaFree(a.log); cudaFree(a.n_logged);
+    cudaFree(f->dU); cudaFree(f->dY); cudaFree(f->dstatus); cudaFree(f->dstats);
+    delete f;
+    return NMPC_OK;
+}
+
+int nmpc_fleet_load(nmpc_fleet* f, const int32_t* n_ref, const double* ref, const int32_t* n_vert, const double* vert,
+                    const double* start, const double* goal, const double* brake_vel, const double* brake_dist,
+                    const double* sched_init, const double* sched) {
+    if (!f) return NMPC_ERR_INVALID;
+    nmpc_handle* h = f->h;
+    const nmpc_fleet_config& fc = f->fc;
+    if (!n_ref || !ref || !n_vert || (!vert && fc.max_vert > 0) || !start || !goal || !brake_vel || !brake_dist ||
+        (fc.n_sched > 0 && (!sched_init || !sched)))
+        return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_load: missing array%s", "");
+    const size_t B = fc.n_robots, N = h->cfg.N_hor, Nd = h->cfg.Ndynobs;
+    for (size_t b = 0; b < B; b++)
+        if (n_ref[b] < 1 || n_ref[b] > fc.max_ref || n_vert[b] < 0 || n_vert[b] > fc.max_vert)
+            return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_load: n_ref / n_vert out of range%s", "");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    FleetArgs& a = f->a;
+#define UP_(dst, src, n) CUDA_TRY(h, cudaMemcpyAsync((void*)(dst), (src), (n), cudaMemcpyHostToDevice, s))
+    UP_(a.n_ref, n_ref, B * sizeof(int32_t));
+    UP_(a.ref, ref, B * fc.max_ref * 3 * sizeof(double));
+    UP_(a.n_vert, n_vert, B * sizeof(int32_t));
+    if (fc.max_vert > 0) UP_(a.vert, vert, B * fc.max_vert * 2 * sizeof(double));
+    UP_(a.goal, goal, B * 3 * sizeof(double));
+    UP_(a.brake_vel, brake_vel, fc.n_brake * sizeof(double));
+    UP_(a.brake_dist, brake_dist, fc.n_brake * sizeof(double));
+    if (fc.n_sched > 0) {
+        UP_(a.sched_init, sched_init, N * Nd * 5 * sizeof(double));
+        UP_(a.sched, sched, (size_t)fc.n_sched * Nd * 5 * sizeof(double));
+    }
+    UP_(a.state, start, B * 3 * sizeof(double));
+#undef UP_
+    CUDA_TRY(h, cudaMemsetAsync(a.last_u, 0, B * 2 * sizeof(double), s));
+    CUDA_TRY(h, cudaMemsetAsync(a.t, 0, B * sizeof(int32_t), s));
+    CUDA_TRY(h, cudaMemsetAsync(a.idx, 0, B * sizeof(int32_t), s));
+    CUDA_TRY(h, cudaMemsetAsync(a.done, 0, B * sizeof(int32_t), s));
+    CUDA_TRY(h, cudaMemsetAsync(a.P, 0, B * h->np * sizeof(double), s));
+    CUDA_TRY(h, cudaMemsetAsync(f->dU, 0, B * 2 * N * sizeof(double), s));
+    CUDA_TRY(h, cudaMemsetAsync(f->dY, 0, B * 2 * N * sizeof(double), s));
+    CUDA_TRY(h, cudaMemsetAsync(f->dstatus, 0, B * sizeof(int32_t), s));
+    if (a.log) CUDA_TRY(h, cudaMemsetAsync(a.n_logged, 0, B * sizeof(int32_t), s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    f->loaded = true;
+    return NMPC_OK;
+}
+
+int nmpc_fleet_step(nmpc_fleet* f, int32_t n_steps) {
+    if (!f || n_steps < 0) return NMPC_ERR_INVALID;
+    nmpc_handle* h = f->h;
+    if (!f->loaded) return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_step: nmpc_fleet_load has not been called%s", "");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int B = f->fc.n_robots;
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    for (int k = 0; k < n_steps; k++) {
+        fleet_assemble_kernel<<<(B * 32 + 255) / 256, 256, 0, s>>>(f->a);
+        h->launches++;
+        int rc = launch_solve(h, B, f->a.P, f->dU, f->dY, f->dstatus, f->dstats, s, f->a.done);
+        if (rc) return rc;
+        fleet_advance_kernel<<<(B + 255) / 256, 256, 0, s>>>(f->a);
+        h->launches++;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    return NMPC_OK;
+}
+
+#define DOWN_(dst, src, n) if (dst) CUDA_TRY(h, cudaMemcpyAsync((dst), (src), (n), cudaMemcpyDeviceToHost, s))
+int nmpc_fleet_state(nmpc_fleet* f, double* state, double* last_u, int32_t* t, int32_t* idx, int32_t* done, int32_t* status) {
+    if (!f) return NMPC_ERR_INVALID;
+    nmpc_handle* h = f->h;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t B = f->fc.n_robots;
+    DOWN_(state, f->a.state, B * 3 * sizeof(double));
+    DOWN_(last_u, f->a.last_u, B * 2 * sizeof(double));
+    DOWN_(t, f->a.t, B * sizeof(int32_t));
+    DOWN_(idx, f->a.idx, B * sizeof(int32_t));
+    DOWN_(done, f->a.done, B * sizeof(int32_t));
+    DOWN_(status, f->dstatus, B * sizeof(int32_t));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return NMPC_OK;
+}
+
+int nmpc_fleet_last(nmpc_fleet* f, double* P, double* U, double* Y) {
+    if (!f) return NMPC_ERR_INVALID;
+    nmpc_handle* h = f->h;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t B = f->fc.n_robots, n2 = 2 * (size_t)h->cfg.N_hor;
+    DOWN_(P, f->a.P, B * h->np * sizeof(double));
+    DOWN_(U, f->dU, B * n2 * sizeof(double));
+    DOWN_(Y, f->dY, B * n2 * sizeof(double));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return NMPC_OK;
+}
+
+int nmpc_fleet_log(nmpc_fleet* f, double* log, int32_t* n_logged) {
+    if (!f) return NMPC_ERR_INVALID;
+    nmpc_handle* h = f->h;
+    if (!f->a.log) return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_log: the fleet was created with log_steps = 0%s", "");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t B = f->fc.n_robots;
+    DOWN_(log, f->a.log, B * f->fc.log_steps * 5 * sizeof(double));
+    DOWN_(n_logged, f->a.n_logged, B * sizeof(int32_t));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return NMPC_OK;
+}
+#undef DOWN_
 
 #ifdef NMPC_PROFILE
 void nmpc_debug_set_buffer(void* p) { g_dbg = (long long*)p; }

@@ -291,16 +291,18 @@ class Scenario:
             + self.dyn_constraints + refs
         return np.asarray(p, dtype=np.float64)
 
-    def apply(self, u):
+    def apply(self, u, sincos=None):
         """take num_steps_taken controls and integrate the plant (src/mpc/mpc_generator.py:223-235);
-        returns True when the run is terminal (src/path_generator.py:397)."""
+        returns True when the run is terminal (src/path_generator.py:397).  `sincos(theta) -> (sin, cos)`
+        replaces libm's (the reference's math.sin/math.cos) when a caller needs the device's own trig."""
         cfg = self.cfg
         u = [float(x) for x in u]
         self.system_input += u[:cfg.nu * cfg.num_steps_taken]
         for i in range(cfg.num_steps_taken):
             uv, uw = u[i * cfg.nu], u[1 + i * cfg.nu]
             x, y, th = self.states[-3], self.states[-2], self.states[-1]
-            self.states += [x + cfg.ts * (uv * math.cos(th)), y + cfg.ts * (uv * math.sin(th)), th + cfg.ts * uw]
+            sn, cs = (math.sin(th), math.cos(th)) if sincos is None else sincos(th)
+            self.states += [x + cfg.ts * (uv * cs), y + cfg.ts * (uv * sn), th + cfg.ts * uw]
         self.t += cfg.num_steps_taken
         return self.terminal()
 

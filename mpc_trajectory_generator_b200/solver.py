@@ -142,6 +142,7 @@ class NmpcSolver:
             raise NmpcError(f"nmpc_create failed (rc={rc}): no usable CUDA device {device} or unsupported "
                             f"config; this solver has no CPU fallback")
         self._h = h
+        self._fleets = []   # weak references to NmpcFleet objects created on this handle (closed before it)
 
     # -- lifecycle (mng.start/ping/kill, src/path_generator.py:220-222,408,417) ----------
     def ping(self):
@@ -150,6 +151,10 @@ class NmpcSolver:
 
     def close(self):
         if getattr(self, "_h", None):
+            for ref in getattr(self, "_fleets", []):
+                f = ref()
+                if f is not None:
+                    f.close()
             self._lib.nmpc_destroy(self._h)
             self._h = None
 

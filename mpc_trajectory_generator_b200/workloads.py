@@ -72,7 +72,7 @@ def first_step_batch(host_cfg, complexity=3, B=4096, seed=0):
     return P, scs
 
 
-def closed_loop_batch(host_cfg, solve_fn, complexity=11, robots=256, steps=256, seed=1):
+def closed_loop_batch(host_cfg, solve_fn, complexity=11, robots=256, steps=256, seed=1, sincos=None):
     """BASELINE config 3/4.  Rolls `robots` receding-horizon runs for up to `steps` steps;
     `solve_fn(P, U0, Y0) -> (U, Y, status)` solves one step for all live robots (the reference
     sends only p and the server keeps (u, y): warm start from the previous reply, un-shifted).
@@ -94,8 +94,36 @@ def closed_loop_batch(host_cfg, solve_fn, complexity=11, robots=256, steps=256, 
         rec["robot"].append(ids.copy()); rec["step"].append(np.full(len(ids), k))
         Uprev[ids], Yprev[ids] = U, Y
         for j, i in enumerate(ids):
-            if scs[i].apply(U[j]):
+            if scs[i].apply(U[j], sincos=sincos):
                 live[i] = False
+    return {k: np.concatenate(v) for k, v in rec.items()}
+
+
+def closed_loop_batch_device(solver, host_cfg, complexity=11, robots=256, steps=256, seed=1):
+    """BASELINE config 3/4 recorded on the device: the fleet API rolls `robots` receding-horizon runs for `steps`
+    steps and every live robot's step is recorded as one row (p_k, warm start u_{k-1}, y_{k-1}) -> replay batch.
+    -> dict(P, U0, Y0, U, status, robot, step)"""
+    from .fleet import FleetPlan, NmpcFleet
+    scs = random_scenarios(host_cfg, complexity, robots, seed)
+    plan = FleetPlan.from_scenarios(scs, max_steps=steps)
+    fleet = NmpcFleet(solver, plan)
+    n2 = 2 * host_cfg.N_hor
+    Uprev = np.zeros((robots, n2))
+    Yprev = np.zeros((robots, n2))
+    rec = {k: [] for k in ("P", "U0", "Y0", "U", "status", "robot", "step")}
+    done_prev = np.zeros(robots, dtype=np.int32)
+    for k in range(steps):
+        ids = np.nonzero(done_prev == 0)[0]
+        if len(ids) == 0:
+            break
+        fleet.step(1)
+        P, U, Y = fleet.last()
+        st = fleet.state()
+        rec["P"].append(P[ids]); rec["U0"].append(Uprev[ids].copy()); rec["Y0"].append(Yprev[ids].copy())
+        rec["U"].append(U[ids]); rec["status"].append(st["status"][ids]); rec["robot"].append(ids.copy())
+        rec["step"].append(np.full(len(ids), k))
+        Uprev, Yprev, done_prev = U, Y, st["done"]
+    fleet.close()
     return {k: np.concatenate(v) for k, v in rec.items()}
 
 

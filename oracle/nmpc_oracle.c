@@ -276,7 +276,7 @@ static double eval_psi(staged* S, const double* u, double c, const double* y, do
     const int N = S->N, P = S->P;
     const double ts = S->ts, inv_ts = S->inv_ts;
     const double hc = 0.5 * c, inv_c = 1.0 / fmax(c, 1.0);
-    double tw[MAXT], inclT[MAXT], exclT[MAXT], sn[MAXT], cs[MAXT], a[MAXT], b[MAXT];
+    double tw[MAXT] = {0}, inclT[MAXT], exclT[MAXT], sn[MAXT], cs[MAXT], a[MAXT] = {0}, b[MAXT] = {0};
     double inclA[MAXT], exclA[MAXT], inclB[MAXT], exclB[MAXT];
     double X[MAXT], Y[MAXT], TH[MAXT], thpre[MAXT], xpre[MAXT], ypre[MAXT];
     double gX[MAXT], gY[MAXT], mind2[MAXT], cl[MAXT], Aa[MAXT], Aw[MAXT];
@@ -399,7 +399,7 @@ static double eval_psi(staged* S, const double* u, double c, const double* y, do
     if (!grad) return psi;
 
     /* backward sweep */
-    double mth[MAXT], LX[MAXT], LY[MAXT], nn[MAXT], rr[MAXT], TT[MAXT];
+    double mth[MAXT], LX[MAXT], LY[MAXT], nn[MAXT], rr[MAXT] = {0}, TT[MAXT];
     for (int t = 0; t < N; t++) {
         double qq = (t + 1 < N) ? S->q : S->qN, qt = (t + 1 < N) ? S->qth : S->qthN;
         gX[t] = fma(2.0 * qq, X[t] - S->xref, gX[t]);

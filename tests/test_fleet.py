@@ -1,0 +1,148 @@
+"""Fleet stepping: the device-side receding-horizon loop against the host mirror of the
+reference's loop (host.assembly.Scenario — itself validated bit for bit against the unmodified reference's recorded
+run, tests/test_host_assembly.py) driven by the C oracle.
+
+Bars: the parameter vector every robot assembles on the device equals the host mirror's `parameters()` bit for bit at
+every step; solutions, multipliers, exit flags, plant states and termination flags equal the host loop's bit for bit
+when the host plant uses the solver's sincos (<= 2 ulp from libm; with libm the closed loops agree to ~1e-9 until a
+non-converged solve amplifies the last-bit difference — reported, not asserted)."""
+import numpy as np
+import pytest
+
+from mpc_trajectory_generator_b200 import workloads
+from mpc_trajectory_generator_b200.fleet import FleetPlan
+from mpc_trajectory_generator_b200.host import assembly
+
+
+def _scenarios(complexity, n, seed, **cfgkw):
+    hc = assembly.HostConfig.default(**cfgkw)
+    if complexity in (2, 12):   # maps with dynamic obstacles: the map's own start/goal plus nearby variants
+        gmap = assembly.load_maps()[complexity]
+        rng = np.random.default_rng(seed)
+        out = []
+        env = assembly.Scenario.make_env(hc, gmap)
+        while len(out) < n:
+            s0 = list(gmap["start"])
+            s0[0] += rng.uniform(-0.3, 0.3)
+            s0[1] += rng.uniform(-0.3, 0.3)
+            sc = assembly.Scenario(hc, gmap, s0, gmap["end"], env=env)
+            if sc.ok:
+                out.append(sc)
+        return hc, out
+    return hc, workloads.random_scenarios(hc, complexity, n, seed)
+
+
+def test_plan_packing_cpu():
+    hc, scs = _scenarios(3, 5, seed=4)
+    plan = FleetPlan.from_scenarios(scs)
+    assert plan.n_robots == 5 and plan.ref.shape[2] == 3 and plan.sched is None
+    for b, s in enumerate(scs):
+        n = plan.n_ref[b]
+        assert n == len(s.x_ref)
+        assert np.array_equal(plan.ref[b, :n, 0], s.x_ref) and np.array_equal(plan.ref[b, :n, 2], s.theta_ref)
+        assert plan.n_vert[b] == len(s.vert)
+        assert np.array_equal(plan.goal[b], s.end)
+    assert plan.base_speed == hc.lin_vel_max * hc.throttle_ratio
+    assert plan.circle_radius == hc.vehicle_width / 2 + hc.vehicle_margin
+
+
+def test_dynamic_schedule_matches_ring_cpu():
+    """the closed form 'ring slot j at step t = schedule entry t+j' against the reference's rotate-and-append ring"""
+    hc, scs = _scenarios(12, 1, seed=0)
+    sc = scs[0]
+    N, Nd = hc.N_hor, hc.Ndynobs
+    plan = FleetPlan.from_scenarios(scs, max_steps=30)
+    off = 20 + N + 3 * hc.Nobs
+    for t in range(30):
+        p = sc.parameters()
+        ring = p[off:off + 5 * Nd * N].reshape(Nd, N, 5)
+        for j in range(N):
+            m = t + j
+            src = plan.sched_init[m] if m < N else plan.sched[m]
+            assert np.array_equal(ring[:, j, :], src), (t, j)
+        sc.apply(np.zeros(2 * N))   # any input: the ring does not depend on the robot
+
+
+def _host_loop(oracle, hc, scs, steps, sincos):
+    """reference loop on the host: parameters() -> oracle solve (persisted un-shifted warm start) -> apply"""
+    ocfg = oracle.default_config(N_hor=hc.N_hor, Nobs=hc.Nobs, Ndynobs=hc.Ndynobs)
+    B, n2 = len(scs), 2 * hc.N_hor
+    U = np.zeros((B, n2))
+    Y = np.zeros((B, n2))
+    live = np.ones(B, dtype=bool)
+    hist = []
+    for k in range(steps):
+        ids = np.nonzero(live)[0]
+        P = np.zeros((B, oracle.param_len(ocfg)))
+        st = np.zeros(B, dtype=np.int32)
+        if len(ids):
+            P[ids] = np.stack([scs[i].parameters() for i in ids])
+            U[ids], Y[ids], st[ids], _ = oracle.solve_batch(ocfg, P[ids], U[ids], Y[ids])
+            for i in ids:
+                if scs[i].apply(U[i], sincos=sincos):
+                    live[i] = False
+        hist.append(dict(P=P.copy(), U=U.copy(), Y=Y.copy(), status=st.copy(), live_before=ids.copy(),
+                         state=np.array([s.states[-3:] for s in scs]), idx=np.array([s.idx for s in scs]),
+                         done=(~live).astype(np.int32)))
+    return hist
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("complexity,B,steps", [(3, 24, 12), (12, 6, 25), (1, 8, 10)])
+def test_fleet_steps_match_host_loop(oracle, gpu_solver_factory, complexity, B, steps):
+    import mpc_trajectory_generator_b200 as pkg
+    hc, scs = _scenarios(complexity, B, seed=10 + complexity)
+    plan = FleetPlan.from_scenarios(scs, max_steps=steps)
+    solver = gpu_solver_factory(workloads.solver_config_for(hc))
+    fleet = pkg.NmpcFleet(solver, plan, log_steps=steps)
+
+    def sincos(th):
+        s, c = oracle.sincos(th)
+        return s, c
+    hist = _host_loop(oracle, hc, scs, steps, sincos)
+    for k in range(steps):
+        fleet.step(1)
+        P, U, Y = fleet.last()
+        st = fleet.state()
+        h = hist[k]
+        ids = h["live_before"]
+        assert np.array_equal(P[ids], h["P"][ids]), f"step {k}: assembled parameters differ"
+        assert np.array_equal(st["status"][ids], h["status"][ids]), f"step {k}: exit flags differ"
+        assert np.array_equal(U[ids], h["U"][ids]), f"step {k}: solutions differ"
+        assert np.array_equal(Y[ids], h["Y"][ids]), f"step {k}: multipliers differ"
+        assert np.array_equal(st["state"], h["state"]), f"step {k}: plant states differ"
+        assert np.array_equal(st["idx"][ids], h["idx"][ids])
+        assert np.array_equal(st["done"], h["done"])
+    lg, n = fleet.log()
+    assert np.array_equal(n, st["t"])
+    b = 0
+    assert np.array_equal(lg[b, :n[b], 0:3], np.array(scs[b].states[3:]).reshape(-1, 3)[:n[b]])
+    fleet.close()
+
+
+@pytest.mark.gpu
+def test_fleet_run_to_goal_multi_step_launch(oracle, gpu_solver_factory):
+    """n steps in one call == n calls of one step; a whole run on the reference's default scenario terminates at the
+    goal like the host loop (same step count, same final state)."""
+    import mpc_trajectory_generator_b200 as pkg
+    hc = assembly.HostConfig.default()
+    gmap = assembly.load_maps()[1]
+    scs = [assembly.Scenario(hc, gmap)]
+    plan = FleetPlan.from_scenarios(scs)
+    solver = gpu_solver_factory(workloads.solver_config_for(hc))
+    fa = pkg.NmpcFleet(solver, plan, log_steps=400)
+    fb = pkg.NmpcFleet(solver, plan, log_steps=400)
+    fa.step(40)
+    for _ in range(40):
+        fb.step(1)
+    sa, sb = fa.state(), fb.state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    fa.step(260)
+    sa = fa.state()
+    assert sa["done"][0] == 1, "the default scenario reaches its goal within 300 steps"
+    hist = _host_loop(oracle, hc, scs, int(sa["t"][0]), lambda th: oracle.sincos(th))
+    assert hist[-1]["done"][0] == 1 and (len(hist) < 2 or hist[-2]["done"][0] == 0)
+    assert np.array_equal(hist[-1]["state"][0], sa["state"][0])
+    fa.close()
+    fb.close()
