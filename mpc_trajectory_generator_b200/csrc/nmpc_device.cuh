@@ -29,6 +29,27 @@
 #ifndef NMPC_CTE_STAGE
 #define NMPC_CTE_STAGE 0
 #endif
+// Code size matters as much as instruction count here: the per-iteration hot loop of the solver is about the
+// size of the SM's 32 KB L1.5 instruction cache, and a loop that no longer fits misses on every line (measured:
+// a lone warp's two-loop recursion slows from 5.7k to 7.9k cycles when the evaluation code grows by 15 %).
+// NMPC_UNROLL_LOOPS=1 lets ptxas unroll the latency-bound loops again (tools/variants.py).
+#ifndef NMPC_UNROLL_LOOPS
+#define NMPC_UNROLL_LOOPS 0
+#endif
+#if NMPC_UNROLL_LOOPS
+#define NMPC_NOUNROLL
+#else
+#define NMPC_NOUNROLL _Pragma("unroll 1")
+#endif
+// the five exchange stages of every warp reduction / scan: unrolled (1) or a real loop (0, smaller code)
+#ifndef NMPC_STAGE_UNROLL
+#define NMPC_STAGE_UNROLL 1
+#endif
+#if NMPC_STAGE_UNROLL
+#define NMPC_STAGES _Pragma("unroll")
+#else
+#define NMPC_STAGES _Pragma("unroll 1")
+#endif
 #ifndef NMPC_LB_PREFETCH
 #define NMPC_LB_PREFETCH 1
 #endif
@@ -55,17 +76,37 @@ extern __shared__ __align__(16) double smem[];
 
 // ---------------------------------------------------------------------------------
 // per-warp shared-memory arena (offsets in doubles; every block is 16-byte aligned)
-enum { V_GRAD = 0, V_UHALF, V_FPR, V_DIR, V_GSTEP, V_OLDS, V_OLDG, V_S, V_Y = V_S + MEMP1, V_END = V_Y + MEMP1 };
+#ifndef NMPC_HELP_EXTRA
+#define NMPC_HELP_EXTRA 9  // trials offered beyond what the previous search needed (9 = always all NMPC_HELP_R)
+#endif
+#ifndef NMPC_HELP_MODE
+#define NMPC_HELP_MODE 0
+#endif
+#ifndef NMPC_HELP_SLEEP
+#define NMPC_HELP_SLEEP 100  // ns between two polls of an idle helper
+#endif
+// Speculative line search on idle warps (experiments/README.md has the measurements): once the problem queue is
+// empty, warps without a problem evaluate the next line-search trials of the warps that still have one.  Bit-exact
+// and 10 % faster for a lone problem, +2..6 % on the B=4096 batch, but the extra ~800 instructions push the hot
+// loop further past the 32 KB instruction cache and cost 2.7 % when every warp owns a problem -> off by default.
+#ifndef NMPC_HELP_R
+#define NMPC_HELP_R 0  // line-search trials a problem may have in flight on idle warps of its CTA (0 = feature off)
+#endif
+enum { V_GRAD = 0, V_UHALF, V_FPR, V_DIR, V_GSTEP, V_OLDS, V_OLDG, V_S, V_Y = V_S + MEMP1,
+       V_U = V_Y + MEMP1, V_YL, V_JG, V_END = V_JG + NMPC_HELP_R };  // V_U, V_YL, V_JG*: what a helper warp reads / writes
 enum { H_X0 = 0, H_Y0, H_TH0, H_VINIT, H_WINIT, H_XREF, H_YREF, H_THREF, H_Q, H_QV, H_QTH, H_RV, H_RW, H_QN, H_QTHN,
        H_QCTE, H_AP, H_WP, H_INVTS,
        // warp-uniform solver state that is touched once per outer iteration (kept out of the registers)
-       H_F2N, H_DYN, H_F2NP, H_DYNP, H_NORMH, H_LIP, H_AKKT, H_COUNT = 26 };
+       H_F2N, H_DYN, H_F2NP, H_DYNP, H_NORMH, H_LIP, H_AKKT, H_NCIRC /* int */, H_COUNT = 28 };
+// job record of one speculative line-search trial (bytes): state, trial, seq (ints) | gamma | c | psi | lhs
+#define JOB_BYTES 64u
+enum { JOB_EMPTY = 0, JOB_POSTED = 1, JOB_TAKEN = 2, JOB_DONE = 3 };
 #define SEG_STRIDE 6   // s1x s1y | dx dy | inv pad
 #define CIRC_STRIDE 4  // cx cy | r2 (original slot index as int in the 4th double)
 #define ELL_STRIDE 6   // ex ey | cosA sinA | 1/rx^2 1/ry^2
 
 struct Lay {
-    int n2, seg, circ, ell, rho, alpha, hdr, vref, total;
+    int n2, seg, circ, ell, rho, alpha, hdr, vref, job, total;
 };
 __host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
 __host__ __device__ inline Lay make_layout(int N, int Nobs, int Nd) {
@@ -79,6 +120,7 @@ __host__ __device__ inline Lay make_layout(int N, int Nobs, int Nd) {
     L.alpha = o; o += 12;
     L.hdr = o; o += H_COUNT;
     L.vref = o; o += even_up(N);
+    L.job = o; o += (NMPC_HELP_R > 0 ? NMPC_HELP_R : 1) * (int)(JOB_BYTES / 8);
     L.total = o;
     return L;
 }
@@ -128,6 +170,24 @@ __device__ __forceinline__ void sts2(uint32_t a, double2 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
 }
 __device__ __forceinline__ void stsi(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// volatile / atomic access to the job words shared between warps of one CTA
+__device__ __forceinline__ int ldv_shared(uint32_t a) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stv_shared(uint32_t a, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ int cas_shared(uint32_t a, int cmp, int val) {
+    int old;
+    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ int add_shared(uint32_t a, int val) {
+    int old;
+    asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(val) : "memory");
+    return old;
+}
 
 // Rectangle::project of OpEn is comparison-based: a NaN stays a NaN (and ends the solve as NotFinite)
 __device__ __forceinline__ double clampd(double x, double lo, double hi) { return (x < lo) ? lo : ((x > hi) ? hi : x); }
@@ -209,7 +269,7 @@ __device__ __forceinline__ void nm_sincos(double x, double& s, double& c) {
 // ---------------------------------------------------------------------------------
 // warp-ordered reductions
 __device__ __forceinline__ double butterfly(double a) {
-#pragma unroll
+    NMPC_STAGES
     for (int off = 16; off; off >>= 1) a = a + __shfl_xor_sync(FULL, a, off);
     return a;
 }
@@ -229,7 +289,7 @@ __device__ __forceinline__ void hsum2(const double (&e)[P], const double (&f)[P]
         a = a + e[j];
         b = b + f[j];
     }
-#pragma unroll
+    NMPC_STAGES
     for (int off = 16; off; off >>= 1) {
         double ya = __shfl_xor_sync(FULL, a, off), yb = __shfl_xor_sync(FULL, b, off);
         a = a + ya;
@@ -250,7 +310,7 @@ __device__ __forceinline__ void hsum4(const double (&e0)[P], const double (&e1)[
         c = c + e2[j];
         d = d + e3[j];
     }
-#pragma unroll
+    NMPC_STAGES
     for (int off = 16; off; off >>= 1) {
         double ya = __shfl_xor_sync(FULL, a, off), yb = __shfl_xor_sync(FULL, b, off);
         double yc = __shfl_xor_sync(FULL, c, off), yd = __shfl_xor_sync(FULL, d, off);
@@ -270,7 +330,7 @@ __device__ __forceinline__ void prefix_scan(const double (&x)[P], double (&incl)
 #pragma unroll
     for (int j = 0; j < P; j++) {
         double l = x[j];
-#pragma unroll
+        NMPC_STAGES
         for (int off = 1; off < 32; off <<= 1) {
             double y = __shfl_up_sync(FULL, l, off);
             add_if(l, y, lane >= off);
@@ -289,7 +349,7 @@ __device__ __forceinline__ void prefix_scan2(const double (&xa)[P], const double
 #pragma unroll
     for (int j = 0; j < P; j++) {
         double la = xa[j], lb = xb[j];
-#pragma unroll
+        NMPC_STAGES
         for (int off = 1; off < 32; off <<= 1) {
             double ya = __shfl_up_sync(FULL, la, off);
             double yb = __shfl_up_sync(FULL, lb, off);
@@ -314,7 +374,7 @@ __device__ __forceinline__ void suffix_scan(const double (&x)[P], double (&suf)[
 #pragma unroll
     for (int j = P - 1; j >= 0; j--) {
         double l = x[j];
-#pragma unroll
+        NMPC_STAGES
         for (int off = 1; off < 32; off <<= 1) {
             double y = __shfl_down_sync(FULL, l, off);
             add_if(l, y, lane + off < 32);
@@ -331,7 +391,7 @@ __device__ __forceinline__ void suffix_scan2(const double (&xa)[P], const double
 #pragma unroll
     for (int j = P - 1; j >= 0; j--) {
         double la = xa[j], lb = xb[j];
-#pragma unroll
+        NMPC_STAGES
         for (int off = 1; off < 32; off <<= 1) {
             double ya = __shfl_down_sync(FULL, la, off);
             double yb = __shfl_down_sync(FULL, lb, off);
@@ -360,7 +420,7 @@ __device__ __forceinline__ void suffix_scan2_hsum(const double (&xa)[P], const d
 #pragma unroll
     for (int j = P - 1; j >= 0; j--) {
         double la = xa[j], lb = xb[j];
-#pragma unroll
+        NMPC_STAGES
         for (int st = 0; st < 5; st++) {
             const int off = 1 << st;
             double ya = __shfl_down_sync(FULL, la, off);
@@ -421,7 +481,8 @@ struct Warp {
     uint32_t sb;         // shared byte address of the arena
     uint32_t la[P];      // sb + 16*t : this lane's element inside vector 0
     uint32_t vstride;    // bytes per vector (2N doubles)
-    uint32_t a_seg, a_circ, a_ell, a_rho, a_alpha, a_hdr, a_vref;
+    uint32_t a_seg, a_circ, a_ell, a_rho, a_alpha, a_hdr, a_vref, a_job;
+    uint32_t sb0, arena_bytes;  // arena of warp 0 / bytes per arena (retarget)
     int lane, n_circ;    // n_circ: circles with r != 0 (zero-padded slots are skipped: they add exact zeros)
     bool act[P];
     int tix[P];
@@ -430,10 +491,12 @@ struct Warp {
 #endif
 
     __device__ __forceinline__ Warp(const nmpc_config& c, const Lay& L, int warp, int lane_) : cfg(c), lane(lane_) {
-        sb = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)(warp * L.total) * 8u;
+        sb0 = (uint32_t)__cvta_generic_to_shared(smem);
+        arena_bytes = (uint32_t)L.total * 8u;
+        sb = sb0 + (uint32_t)warp * arena_bytes;
         vstride = (uint32_t)L.n2 * 8u;
         a_seg = sb + L.seg * 8u; a_circ = sb + L.circ * 8u; a_ell = sb + L.ell * 8u; a_rho = sb + L.rho * 8u;
-        a_alpha = sb + L.alpha * 8u; a_hdr = sb + L.hdr * 8u; a_vref = sb + L.vref * 8u;
+        a_alpha = sb + L.alpha * 8u; a_hdr = sb + L.hdr * 8u; a_vref = sb + L.vref * 8u; a_job = sb + L.job * 8u;
         n_circ = 0;
 #pragma unroll
         for (int j = 0; j < P; j++) {
@@ -441,6 +504,15 @@ struct Warp {
             act[j] = tix[j] < (NF ? NF : cfg.N_hor);
             la[j] = sb + 16u * tix[j];
         }
+    }
+    // point this view at the arena of warp `o` of the CTA (a helper warp evaluates another warp's problem there)
+    __device__ __forceinline__ void retarget(int o) {
+        const uint32_t nsb = sb0 + (uint32_t)o * arena_bytes, d = nsb - sb;
+        sb = nsb;
+        a_seg += d; a_circ += d; a_ell += d; a_rho += d; a_alpha += d; a_hdr += d; a_vref += d; a_job += d;
+#pragma unroll
+        for (int j = 0; j < P; j++) la[j] += d;
+        n_circ = ldsi(a_hdr + 8u * H_NCIRC);
     }
     __device__ __forceinline__ double hdr(int i) const { return lds1(a_hdr + 8u * i); }
     __device__ __forceinline__ void ld(int k, double2 (&r)[P]) const {
@@ -483,6 +555,7 @@ struct Warp {
             nreal += __popc(m);
         }
         n_circ = nreal;
+        if (lane == 0) stsi(a_hdr + 8u * H_NCIRC, nreal);
         const double* pe = pc + 3 * Nobs;
         const int ne = Nd * N;
         for (int i = lane; i < ne; i += 32) {
@@ -602,6 +675,7 @@ struct Warp {
             int i = 1;
             // UNR segments per trip, written stage by stage: the SM issues in order, so independent
             // chains only overlap if they are interleaved in the instruction stream
+            NMPC_NOUNROLL
             for (; i + UNR <= N; i += UNR, as += 48u * UNR) {
                 double2 s1[UNR], d[UNR];
                 double inv[UNR];
@@ -922,11 +996,17 @@ struct Warp {
 // Phases that end in an evaluation set (x, mode) and fall through to it; the others `continue`.
 enum Phase {
     PH_OUTER_BEGIN, PH_INIT_A, PH_INIT_B, PH_STEP_BEGIN, PH_LIP, PH_COST_U, PH_LIP_LOOP, PH_LIP_RETRY, PH_IT0, PH_LS,
-    PH_STEP_DONE, PH_SOLVE_END, PH_F2, PH_FINAL, PH_EXIT
+    PH_STEP_DONE, PH_SOLVE_END, PH_F2, PH_FINAL, PH_EXIT, PH_HELP_WAIT, PH_HELP_EVAL
 };
 
+// Owner mode (helper == false) solves the staged problem.  Helper mode (entered once the problem queue is empty)
+// serves the other warps of the CTA: it polls their job records for posted line-search trials
+// x = u - (1-tau) fpr - tau dir, evaluates them in the owner's arena through the same evaluation site and writes
+// back psi, the gradient and the trial's envelope value; it returns when no warp of the CTA owns a problem any
+// more.  Who evaluates a trial never changes its bits, so results do not depend on timing.
 template <int P, int NF>
-__device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], nmpc_stats& st_out, long long* prof_out = nullptr) {
+__device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], nmpc_stats& st_out, const bool helper,
+                             const uint32_t a_live, const int nwarps, long long* prof_out = nullptr) {
 #ifdef NMPC_PROFILE
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long tstart = clock64();
@@ -956,15 +1036,18 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
     bool cont = true, fbe_valid = false;
     double fbe_u = 0.0;
     const double inv_ts = W.hdr(H_INVTS);
+    int ls_hint = 0;  // trials the previous line search needed beyond tau = 1
+    int ls_seq = 0;   // owner: line searches started (tags job records); helper: slot r of the job being served
 
     double2 x[P], g[P];  // evaluation point / gradient out
     double pen = 0.0;
     int mode = MODE_GRAD;
-    int phase = PH_OUTER_BEGIN;
+    int phase = helper ? PH_HELP_WAIT : PH_OUTER_BEGIN;
 
-    auto set_gamma = [&](double gm) {
+    auto set_gamma = [&](double gm) {  // sigma only changes with gamma: computed here, not once per iteration
         gamma = gm;
         inv_gamma = 1.0 / gm;
+        sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * gm);
     };
     // gradient_step() + half_step(): gstep = p - gamma*grad ; uhalf = Proj_U(gstep); both stored
     auto grad_step_half = [&](const double2(&p)[P], const double2(&gr)[P], double2(&gs)[P], double2(&uh)[P]) {
@@ -1003,6 +1086,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                     yl[j].x = clampd(yl[j].x, -Y_SET_BOUND, Y_SET_BOUND);
                     yl[j].y = clampd(yl[j].y, -Y_SET_BOUND, Y_SET_BOUND);
                 }
+                if (NMPC_HELP_R > 0) W.st(V_YL, yl);  // helper warps read the multipliers from the arena
                 // panoc init
                 lb_active = 0;
                 lb_first = 1;
@@ -1085,7 +1169,6 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                     phase = PH_LIP_RETRY;
                     break;
                 }
-                sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * gamma);
                 // lbfgs_direction(): update_hessian(g = fpr, state = u)
                 if (lb_first) {
                     lb_first = 0;
@@ -1135,6 +1218,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                     W.ld(V_S + sl, sv);
                     W.ld(V_Y + sl, yv);
                     double rho = lds1(W.a_rho + 8u * sl);
+                    NMPC_NOUNROLL
                     for (int k = 0; k < lb_active; k++) {
                         const int sl_n = slot((k + 1 < lb_active) ? k + 1 : k);
                         W.ld(V_S + sl_n, sn);
@@ -1158,6 +1242,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                         q[j].y = q[j].y * lb_gamma;
                     }
                     // (sv, yv, rho) now hold the newest pair (k = lb_active-1): the backward loop starts there
+                    NMPC_NOUNROLL
                     for (int k = lb_active - 1; k >= 0; k--) {
                         const int sl_n = slot((k > 0) ? k - 1 : 0);
                         W.ld(V_S + sl_n, sn);
@@ -1178,6 +1263,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 }
 #else
                 if (lb_active > 0) {
+                    NMPC_NOUNROLL
                     for (int k = 0; k < lb_active; k++) {
                         const int sl = slot(k);
                         double2 sv[P], yv[P];
@@ -1197,6 +1283,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                         q[j].x = q[j].x * lb_gamma;
                         q[j].y = q[j].y * lb_gamma;
                     }
+                    NMPC_NOUNROLL
                     for (int k = lb_active - 1; k >= 0; k--) {
                         const int sl = slot(k);
                         double2 sv[P], yv[P];
@@ -1242,6 +1329,35 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 }
                 tau = 1.0;
                 nls = 0;
+#if NMPC_HELP_R > 0
+                ls_seq++;
+                // a_live[0]: warps of the CTA in owner mode; a_live[1..4]: the same per SM sub-partition (warp % 4).
+                // Helpers only work from a sub-partition without owners, so they never take issue slots or FP64
+                // pipe cycles from a warp that is solving a problem.
+                const bool idle_part = __any_sync(FULL, lane < 4 && lane < nwarps && ldv_shared(a_live + 4u + 4u * lane) == 0);
+                if (idle_part) {
+                    // offer the next trials (tau = 1/2, 1/4, ...) while this warp evaluates tau = 1.
+                    // A record still held by a late helper of an earlier search is skipped.
+                    W.st(V_U, u);
+                    __threadfence_block();
+                    __syncwarp();
+                    // offer as many trials as the previous search needed plus one: a search that accepts tau = 1
+                    // leaves nothing running behind it (late helpers slow the owner's shuffles down)
+                    if (lane < NMPC_HELP_R && lane < ls_hint + NMPC_HELP_EXTRA) {
+                        const uint32_t aj = W.a_job + JOB_BYTES * lane;
+                        const int stt = ldv_shared(aj);
+                        if (stt == JOB_EMPTY || stt == JOB_DONE) {
+                            stsi(aj + 4u, lane + 1);
+                            stsi(aj + 8u, ls_seq);
+                            sts1(aj + 16u, gamma);
+                            sts1(aj + 24u, pn.c);
+                            __threadfence_block();
+                            stv_shared(aj, JOB_POSTED);
+                        }
+                    }
+                    __syncwarp();
+                }
+#endif
 #pragma unroll
                 for (int j = 0; j < P; j++) {  // tau = 1: u - 0*fpr - 1*dir
                     x[j].x = fma(-tau, q[j].x, fma(-0.0, fpr[j].x, u[j].x));
@@ -1280,6 +1396,78 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 phase = PH_F2;
                 break;
             }
+#if NMPC_HELP_R > 0
+            case PH_HELP_WAIT: {
+                // poll the job records of every warp of the CTA: lane l looks at record (r, o) = (l / nwarps, l % nwarps),
+                // so the lowest set bit of the vote is the most urgent trial (smallest r) on offer
+                const int njobs = nwarps * NMPC_HELP_R;
+                int j = -1;
+                const uint32_t a_part = a_live + 4u + 4u * ((threadIdx.x >> 5) & 3u);  // this warp's sub-partition
+                for (;;) {
+                    if (ldv_shared(a_live) <= 0) return 0;
+                    if (ldv_shared(a_part) > 0) {  // an owner shares this sub-partition: stay out of its way
+#if NMPC_HELP_MODE >= 1
+                        return 0;
+#endif
+                        __nanosleep(2000);
+                        continue;
+                    }
+#if NMPC_HELP_MODE >= 2
+                    if ((threadIdx.x >> 5) >= 4) return 0;
+#endif
+                    unsigned m = 0;
+                    int base = 0;
+                    for (; base < njobs && !m; base += 32) {
+                        const int l = base + lane;
+                        bool posted = false;
+                        if (l < njobs) {
+                            const int o = l % nwarps, r = l / nwarps;
+                            posted = ldv_shared(W.sb0 + (uint32_t)o * W.arena_bytes + (W.a_job - W.sb) + JOB_BYTES * r) == JOB_POSTED;
+                        }
+                        m = __ballot_sync(FULL, posted);
+                    }
+                    if (m) {
+                        const int l = base - 32 + __ffs(m) - 1;
+                        const int o = l % nwarps, r = l / nwarps;
+                        int ok = 0;
+                        if (lane == 0)
+                            ok = cas_shared(W.sb0 + (uint32_t)o * W.arena_bytes + (W.a_job - W.sb) + JOB_BYTES * r, JOB_POSTED,
+                                            JOB_TAKEN) == JOB_POSTED;
+                        ok = __shfl_sync(FULL, ok, 0);
+                        if (ok) {
+                            j = l;
+                            break;
+                        }
+                        continue;
+                    }
+                    __nanosleep(NMPC_HELP_SLEEP);
+                }
+                __threadfence_block();
+                const int o = j % nwarps, r = j / nwarps;
+                W.retarget(o);
+                const uint32_t aj = W.a_job + JOB_BYTES * r;
+                const int trial = ldsi(aj + 4u);
+                set_gamma(lds1(aj + 16u));
+                pn = make_pen(lds1(aj + 24u));
+                ls_seq = r;
+                tau = 1.0;
+                for (int k = 0; k < trial; k++) tau /= 2.0;
+                const double om = 1.0 - tau;
+                double2 uo[P], fpr[P], dir[P];
+                W.ld(V_U, uo);
+                W.ld(V_FPR, fpr);
+                W.ld(V_DIR, dir);
+                W.ld(V_YL, yl);
+#pragma unroll
+                for (int jj = 0; jj < P; jj++) {
+                    x[jj].x = fma(-tau, dir[jj].x, fma(-om, fpr[jj].x, uo[jj].x));
+                    x[jj].y = fma(-tau, dir[jj].y, fma(-om, fpr[jj].y, uo[jj].y));
+                }
+                mode = MODE_GRAD;
+                phase = PH_HELP_EVAL;
+                break;
+            }
+#endif
             case PH_EXIT: {
 #ifdef NMPC_PROFILE
                 prof[6] = clock64() - tstart;
@@ -1348,7 +1536,6 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 const double lip = sqrt(wdiff2<P>(g, gr)) / sget(H_NORMH);
                 sput(H_LIP, lip);
                 set_gamma(GAMMA_L_COEFF / fmax(lip, MIN_L_ESTIMATE));
-                sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * gamma);
                 grad_step_half(u, gr, gs, uh);
                 num_iter = 0;
                 cont = true;
@@ -1407,8 +1594,9 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                     }
                     hsum2<P>(e, f, d2, gg);
                 }
-                const double lhs = cost - (0.5 * gamma) * gg + (0.5 * d2) * inv_gamma;
-                if (lhs > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS) {
+                double lhs = cost - (0.5 * gamma) * gg + (0.5 * d2) * inv_gamma;
+                bool evaluate = false;
+                while (lhs > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS) {
                     tau /= 2.0;
                     nls++;
                     const double om = 1.0 - tau;
@@ -1420,12 +1608,62 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                         x[j].x = fma(-tau, dir[j].x, fma(-om, fpr[j].x, u[j].x));
                         x[j].y = fma(-tau, dir[j].y, fma(-om, fpr[j].y, u[j].y));
                     }
+#if NMPC_HELP_R > 0
+                    // was this trial offered to a helper?  DONE: take its result; TAKEN: wait for it;
+                    // POSTED: nobody picked it up -> withdraw it and evaluate here.
+                    const int r = (nls - 1) % NMPC_HELP_R;
+                    const uint32_t aj = W.a_job + JOB_BYTES * r;
+                    int got = 0;
+                    if (lane == 0) {
+                        int stt = ldv_shared(aj);
+                        if (stt != JOB_EMPTY && ldsi(aj + 4u) == nls && ldsi(aj + 8u) == ls_seq) {
+                            if (stt == JOB_POSTED && cas_shared(aj, JOB_POSTED, JOB_EMPTY) == JOB_POSTED) stt = JOB_EMPTY;
+                            if (stt != JOB_EMPTY) {
+                                while (ldv_shared(aj) != JOB_DONE) __nanosleep(20);
+                                got = 1;
+                            }
+                        }
+                    }
+                    got = __shfl_sync(FULL, got, 0);
+                    if (got) {
+                        __threadfence_block();
+                        cost = lds1(aj + 32u);
+                        lhs = lds1(aj + 40u);
+                        W.ld(V_JG + r, g);
+                        n_grad++;
+                        __syncwarp();
+                        // the record is free again: offer the trial NMPC_HELP_R steps ahead
+                        if (lane == 0) {
+                            if (nls + NMPC_HELP_R <= MAX_LINESEARCH_ITERATIONS && lhs > rhs_ls &&
+                                nls + NMPC_HELP_R <= ls_hint + NMPC_HELP_EXTRA + 1) {
+                                stsi(aj + 4u, nls + NMPC_HELP_R);
+                                __threadfence_block();
+                                stv_shared(aj, JOB_POSTED);
+                            } else {
+                                stv_shared(aj, JOB_EMPTY);
+                            }
+                        }
+                        if (!(lhs > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) grad_step_half(x, g, gs, uh);  // accepted
+                        continue;
+                    }
+#endif
+                    evaluate = true;
+                    break;
+                }
+                if (evaluate) {
                     mode = MODE_GRAD;
                     phase = PH_LS;
                 } else {
+#if NMPC_HELP_R > 0
+                    if (lane < NMPC_HELP_R) {  // withdraw what is still on offer
+                        const uint32_t aj = W.a_job + JOB_BYTES * lane;
+                        if (ldv_shared(aj) == JOB_POSTED) cas_shared(aj, JOB_POSTED, JOB_EMPTY);
+                    }
+#endif
                     W.st(V_GRAD, g);
 #pragma unroll
                     for (int j = 0; j < P; j++) u[j] = x[j];
+                    ls_hint = nls;
                     fbe_u = lhs;
                     fbe_valid = true;
                     iteration++;
@@ -1433,6 +1671,33 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 }
                 break;
             }
+#if NMPC_HELP_R > 0
+            case PH_HELP_EVAL: {  // helper: envelope value of the trial, results into the owner's arena
+                double e[P], f[P], d2, gg;
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    const double gsx = fma(-gamma, g[j].x, x[j].x), gsy = fma(-gamma, g[j].y, x[j].y);
+                    const double uhx = W.act[j] ? clampd(gsx, cfg.lin_vel_min, cfg.lin_vel_max) : 0.0;
+                    const double uhy = W.act[j] ? clampd(gsy, -cfg.ang_vel_max, cfg.ang_vel_max) : 0.0;
+                    const double d0 = gsx - uhx, d1 = gsy - uhy;
+                    e[j] = fma(d1, d1, d0 * d0);
+                    f[j] = fma(g[j].y, g[j].y, g[j].x * g[j].x);
+                }
+                hsum2<P>(e, f, d2, gg);
+                const double lhs = psi - (0.5 * gamma) * gg + (0.5 * d2) * inv_gamma;
+                const uint32_t aj = W.a_job + JOB_BYTES * ls_seq;
+                W.st(V_JG + ls_seq, g);
+                if (lane == 0) {
+                    sts1(aj + 32u, psi);
+                    sts1(aj + 40u, lhs);
+                }
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) stv_shared(aj, JOB_DONE);
+                phase = PH_HELP_WAIT;
+                break;
+            }
+#endif
             case PH_F2: {  // multipliers y+ = y + c*(F1 - Proj_C(F1 + y/c)); infeasibilities; outer-loop logic
                 double2 yp[P];
                 double e[P];

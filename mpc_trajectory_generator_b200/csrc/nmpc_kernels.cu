@@ -24,33 +24,57 @@ __host__ __device__ constexpr int warps_cap(int P) { return P == 1 ? NMPC_WARPS 
 template <int P, int NF>
 __global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const __grid_constant__ KArgs a) {
     const nmpc_config& cfg = a.cfg;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const Lay L = make_layout(cfg.N_hor, cfg.Nobs, cfg.Ndynobs);
     const int N = NF ? NF : cfg.N_hor;
     Warp<P, NF> W(cfg, L, warp, lane);
+    // warps of this CTA that still own (or may still fetch) a problem; the others serve as helpers
+    // [0] all, [1 + s] those on SM sub-partition s = warp % 4
+    __shared__ int cta_live[5];
+    const uint32_t a_live = (uint32_t)__cvta_generic_to_shared(&cta_live[0]);
+    if (threadIdx.x < 5) cta_live[threadIdx.x] = (threadIdx.x == 0) ? nwarps : (nwarps - (int)threadIdx.x + 1 + 3) / 4;
+    if (lane < (NMPC_HELP_R > 0 ? NMPC_HELP_R : 1)) stsi(W.a_job + JOB_BYTES * lane, JOB_EMPTY);
+    __syncthreads();
+    bool helper = false;
     for (;;) {
         int b = 0;
-        if (lane == 0) b = (int)atomicAdd(a.counter, 1u);
-        b = __shfl_sync(FULL, b, 0);
-        if (b >= a.B) break;
-        if (a.skip && a.skip[b]) continue;
-        W.stage(a.P + (size_t)b * a.np);
+        if (!helper) {
+            if (lane == 0) b = (int)atomicAdd(a.counter, 1u);
+            b = __shfl_sync(FULL, b, 0);
+            if (b >= a.B) {  // queue empty: this warp will not own a problem again
+                if (lane == 0) {
+                    add_shared(a_live + 4u + 4u * (warp & 3), -1);
+                    add_shared(a_live, -1);
+                }
+                if (NMPC_HELP_R == 0 || nwarps == 1 || NMPC_HELP_MODE == 3) break;
+                helper = true;
+            } else if (a.skip && a.skip[b]) {
+                continue;
+            }
+        }
         double2 u[P], yl[P];
-        const double* U0 = a.U + (size_t)b * 2 * N;
-        const double* Y0 = a.Y ? a.Y + (size_t)b * 2 * N : nullptr;
+        if (!helper) {
+            W.stage(a.P + (size_t)b * a.np);
+            const double* U0 = a.U + (size_t)b * 2 * N;
+            const double* Y0 = a.Y ? a.Y + (size_t)b * 2 * N : nullptr;
 #pragma unroll
-        for (int j = 0; j < P; j++) {
-            const int t = lane + 32 * j;
-            u[j] = (t < N) ? *reinterpret_cast<const double2*>(U0 + 2 * t) : make_double2(0.0, 0.0);
-            yl[j] = (t < N && Y0) ? make_double2(Y0[t], Y0[N + t]) : make_double2(0.0, 0.0);
+            for (int j = 0; j < P; j++) {
+                const int t = lane + 32 * j;
+                u[j] = (t < N) ? *reinterpret_cast<const double2*>(U0 + 2 * t) : make_double2(0.0, 0.0);
+                yl[j] = (t < N && Y0) ? make_double2(Y0[t], Y0[N + t]) : make_double2(0.0, 0.0);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < P; j++) u[j] = yl[j] = make_double2(0.0, 0.0);
         }
         nmpc_stats st;
         st.cost = 0.0;
 #ifdef NMPC_PROFILE
-        const int status = solve_problem<P, NF>(W, u, yl, st, a.dbg ? a.dbg + (size_t)b * 16 : nullptr);
+        const int status = solve_problem<P, NF>(W, u, yl, st, helper, a_live, nwarps, a.dbg && !helper ? a.dbg + (size_t)b * 16 : nullptr);
 #else
-        const int status = solve_problem<P, NF>(W, u, yl, st);
+        const int status = solve_problem<P, NF>(W, u, yl, st, helper, a_live, nwarps);
 #endif
+        if (helper) break;  // no warp of the CTA owns a problem any more
 #pragma unroll
         for (int j = 0; j < P; j++) {
             const int t = lane + 32 * j;
@@ -240,7 +264,7 @@ int nmpc_create(const nmpc_config* cfg, int device, nmpc_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     const Lay L = make_layout(cfg->N_hor, cfg->Nobs, cfg->Ndynobs);
     const size_t per_warp = (size_t)L.total * sizeof(double);
-    const size_t max_smem = prop.sharedMemPerBlockOptin;
+    const size_t max_smem = prop.sharedMemPerBlockOptin - 64;  // the kernels keep a few static words as well
     int w = (int)(max_smem / per_warp);
     if (w < 1) {
         delete h;
