@@ -341,7 +341,7 @@ def main():
                        "l2": "flushed between timed iterations (256 MiB write)", "seed": args.seed,
                        "parity": "bit-exact vs oracle/ (tests/test_gpu_parity.py); OpEn itself not runnable here"},
             "ms_per_solve": total_ms_max / args.steps / B,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "ms_per_step": e2e_ms_step, "api": "NmpcSolver.solve_batch_into -> nmpc_solve_batch (C ABI), pinned host buffers"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
