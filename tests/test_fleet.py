@@ -14,8 +14,8 @@ from mpc_trajectory_generator_b200.fleet import FleetPlan
 from mpc_trajectory_generator_b200.host import assembly
 
 
-def _scenarios(complexity, n, seed, **cfgkw):
-    hc = assembly.HostConfig.default(**cfgkw)
+def _scenarios(complexity, n, seed, smooth=False, **cfgkw):
+    hc = assembly.HostConfig.smooth_velocity(**cfgkw) if smooth else assembly.HostConfig.default(**cfgkw)
     if complexity in (2, 12):   # maps with dynamic obstacles: the map's own start/goal plus nearby variants
         gmap = assembly.load_maps()[complexity]
         rng = np.random.default_rng(seed)
@@ -65,7 +65,7 @@ def test_dynamic_schedule_matches_ring_cpu():
 
 def _host_loop(oracle, hc, scs, steps, sincos):
     """reference loop on the host: parameters() -> oracle solve (persisted un-shifted warm start) -> apply"""
-    ocfg = oracle.default_config(N_hor=hc.N_hor, Nobs=hc.Nobs, Ndynobs=hc.Ndynobs)
+    ocfg = _oracle_cfg(oracle, hc)
     B, n2 = len(scs), 2 * hc.N_hor
     U = np.zeros((B, n2))
     Y = np.zeros((B, n2))
@@ -87,11 +87,18 @@ def _host_loop(oracle, hc, scs, steps, sincos):
     return hist
 
 
+def _oracle_cfg(oracle, hc):
+    return oracle.default_config(N_hor=hc.N_hor, Nobs=hc.Nobs, Ndynobs=hc.Ndynobs, ang_vel_max=hc.ang_vel_max,
+                                 ang_acc_max=hc.ang_acc_max, lin_vel_min=hc.lin_vel_min, lin_vel_max=hc.lin_vel_max,
+                                 lin_acc_min=hc.lin_acc_min, lin_acc_max=hc.lin_acc_max, ts=hc.ts)
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("complexity,B,steps", [(3, 24, 12), (12, 6, 25), (1, 8, 10)])
-def test_fleet_steps_match_host_loop(oracle, gpu_solver_factory, complexity, B, steps):
+@pytest.mark.parametrize("complexity,B,steps,smooth,N", [(3, 24, 12, False, 20), (12, 6, 25, False, 20), (1, 8, 10, False, 20),
+                                                         (11, 6, 8, True, 40)])   # last: BASELINE config 4's setup
+def test_fleet_steps_match_host_loop(oracle, gpu_solver_factory, complexity, B, steps, smooth, N):
     import mpc_trajectory_generator_b200 as pkg
-    hc, scs = _scenarios(complexity, B, seed=10 + complexity)
+    hc, scs = _scenarios(complexity, B, seed=10 + complexity, smooth=smooth, N_hor=N)
     plan = FleetPlan.from_scenarios(scs, max_steps=steps)
     solver = gpu_solver_factory(workloads.solver_config_for(hc))
     fleet = pkg.NmpcFleet(solver, plan, log_steps=steps)

@@ -185,6 +185,40 @@ def test_full_size_properties(gpu_solver_factory):
     assert np.array_equal(U3, U[perm]) and np.array_equal(st3, st[perm]) and np.array_equal(Y3, Y[perm])
 
 
+@pytest.mark.parametrize("N,Nobs", [(10, 50), (20, 200), (40, 100), (80, 10)])
+def test_sweep_workload_parity(oracle, gpu_solver_factory, N, Nobs):
+    """BASELINE config 5 grid points (horizon x static-obstacle slots), built by workloads.sweep_batch."""
+    import mpc_trajectory_generator_b200 as pkg
+    from mpc_trajectory_generator_b200 import workloads
+    P, hc = workloads.sweep_batch(N, Nobs, B=10, seed=2)
+    g, o = _cfgs(pkg, oracle, N_hor=N, Nobs=Nobs, Ndynobs=3)
+    s = gpu_solver_factory(g)
+    U, Y, st, stats = s.solve_batch(P)
+    Uo, Yo, sto, statso = oracle.solve_batch(o, P)
+    assert np.array_equal(st, sto)
+    assert np.linalg.norm(U - Uo) <= REL_TOL * np.linalg.norm(Uo)
+    assert np.array_equal(U, Uo) and np.array_equal(Y, Yo)
+    assert np.array_equal(stats["inner_iterations"], statso["inner_iterations"])
+
+
+def test_config2_workload_full_batch_parity(oracle, gpu_solver_factory):
+    """BASELINE config 2 at its full size (B=4096 first-step problems on map 3): every reply against the oracle."""
+    import mpc_trajectory_generator_b200 as pkg
+    from mpc_trajectory_generator_b200 import workloads
+    from mpc_trajectory_generator_b200.host import assembly
+    hc = assembly.HostConfig.default()
+    P, _ = workloads.first_step_batch(hc, complexity=3, B=4096, seed=0)
+    g, o = _cfgs(pkg, oracle)
+    s = gpu_solver_factory(g)
+    U, Y, st, stats = s.solve_batch(P)
+    Uo, Yo, sto, statso = oracle.solve_batch(o, P)
+    assert np.array_equal(st, sto)
+    num = np.linalg.norm(U - Uo, axis=1)
+    assert (num / np.maximum(np.linalg.norm(Uo, axis=1), 1e-12)).max() <= REL_TOL
+    assert np.array_equal(U, Uo) and np.array_equal(Y, Yo)
+    assert np.array_equal(stats["n_grad_evals"], statso["n_grad_evals"])
+
+
 def test_device_pointer_entry(oracle, gpu_solver_factory):
     """nmpc_solve_batch_device on torch tensors / torch's current stream (the path bench.py times)."""
     import torch
