@@ -196,7 +196,8 @@ int nmpc_fleet_destroy(nmpc_fleet* f);
 
 /* Upload the per-robot plans (HOST buffers) and reset every robot to step 0 (state = start, last input 0,
  * reference index 0, warm start zeros):
- *   n_ref[B], ref[B, max_ref, 3]   (x, y, theta) samples of rough_ref (src/mpc/mpc_generator.py:17-57)
+ *   n_ref[B], ref[B, max_ref, 3]   (x, y, theta) samples of rough_ref (src/mpc/mpc_generator.py:17-57);
+ *                                  both NULL if nmpc_fleet_sample_refs produces them on the device
  *   n_vert[B], vert[B, max_vert, 2] original vertices of the A* corners (src/visibility/visibility.py:126-139)
  *   start[B, 3], goal[B, 3]
  *   brake_vel[n_brake], brake_dist[n_brake]     (src/path_generator.py:439-477)
@@ -206,6 +207,15 @@ int nmpc_fleet_destroy(nmpc_fleet* f);
 int nmpc_fleet_load(nmpc_fleet* f, const int32_t* n_ref, const double* ref, const int32_t* n_vert,
                     const double* vert, const double* start, const double* goal, const double* brake_vel,
                     const double* brake_dist, const double* sched_init, const double* sched);
+
+/* sample every robot's reference on the device instead of uploading it — rough_ref
+ * (src/mpc/mpc_generator.py:17-57) walks nodes[b] = path[1:] of the robot's global plan from its start position at
+ * speed v (the reference passes throttle_ratio * 1.1 * lin_vel_max, src/path_generator.py:262-264), one sample per ts.
+ * Call after nmpc_fleet_load (which may then be given ref = NULL); replaces the fleet's ref / n_ref.
+ *   n_nodes[B], nodes[B, max_nodes, 2] HOST; ref_out[B, max_ref, 3], n_ref_out[B] nullable HOST read-back.
+ * Fails with NMPC_ERR_INVALID if a robot needs more than max_ref samples. */
+int nmpc_fleet_sample_refs(nmpc_fleet* f, const int32_t* n_nodes, const double* nodes, int32_t max_nodes, double v,
+                           double* ref_out, int32_t* n_ref_out);
 
 /* run n_steps receding-horizon steps for every robot that has not terminated; synchronous */
 int nmpc_fleet_step(nmpc_fleet* f, int32_t n_steps);

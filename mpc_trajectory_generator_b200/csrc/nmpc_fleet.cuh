@@ -226,3 +226,65 @@ __global__ void __launch_bounds__(256) fleet_advance_kernel(const __grid_constan
     // np.allclose(states[-3:-1], end[0:2], atol=0.05, rtol=0) and abs(system_input[-2]) < 0.005
     if (fabs(x - goal[0]) <= f.fc.goal_tol && fabs(y - goal[1]) <= f.fc.goal_tol && fabs(v) < f.fc.stop_tol) f.done[b] = 1;
 }
+
+// One thread per robot: rough_ref (src/mpc/mpc_generator.py:17-57) — walk the waypoint list at speed v and emit one
+// (x, y, heading) sample per sampling interval.  Same statements in the same order as the reference's loop; hypot and
+// atan2 are CUDA's (<= 2 ulp from the reference's libm), so samples agree to the last bits, not bit for bit.
+struct SampleArgs {
+    int B, max_nodes, max_ref;
+    double v, ts;
+    const int32_t* n_nodes;
+    const double* nodes;   // [B, max_nodes, 2] = path[1:] of the global plan
+    const double* start;   // [B, 3] (the fleet's state array at step 0)
+    double* ref;           // [B, max_ref, 3]
+    int32_t* n_ref;        // samples produced (may exceed max_ref: the caller checks)
+};
+
+__global__ void __launch_bounds__(128) fleet_sample_refs_kernel(const __grid_constant__ SampleArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const double* __restrict__ nd = a.nodes + (size_t)b * a.max_nodes * 2;
+    double* __restrict__ out = a.ref + (size_t)b * a.max_ref * 3;
+    const int nn = a.n_nodes[b];
+    double x = a.start[3 * b], y = a.start[3 * b + 1];
+    int i = 0, n = 0;
+    double tx = nd[0], ty = nd[1];
+    double x_dir = 0.0, y_dir = 0.0;
+    bool traveling = nn > 0;
+    while (traveling) {
+        double t = a.ts;
+        while (t > 0.0) {
+            const double dist = hypot(tx - x, ty - y);
+            if (dist == 0.0) {
+                traveling = false;
+                break;
+            }
+            x_dir = (tx - x) / dist;
+            y_dir = (ty - y) / dist;
+            const double time = dist / a.v;
+            if (time > t) {
+                x = x + x_dir * a.v * t;
+                y = y + y_dir * a.v * t;
+                t = 0.0;
+            } else {
+                x = x + x_dir * a.v * time;
+                y = y + y_dir * a.v * time;
+                t = t - time;
+                i++;
+                if (i > nn - 1) {
+                    traveling = false;
+                    break;
+                }
+                tx = nd[2 * i];
+                ty = nd[2 * i + 1];
+            }
+        }
+        if (n < a.max_ref) {
+            out[3 * n] = x;
+            out[3 * n + 1] = y;
+            out[3 * n + 2] = atan2(y_dir, x_dir);
+        }
+        n++;
+    }
+    a.n_ref[b] = n;
+}

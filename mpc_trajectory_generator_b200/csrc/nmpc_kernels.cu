@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <new>
+#include <vector>
 
 #include "nmpc_device.cuh"
 #include "nmpc_fleet.cuh"
@@ -491,7 +492,8 @@ struct nmpc_fleet {
     nmpc_stats* dstats;
     double *dU, *dY;
     int32_t* dstatus;
-    bool loaded;
+    bool loaded;  // plans complete (references uploaded or sampled)
+    bool staged;  // nmpc_fleet_load has run
 };
 
 template <typename T>
@@ -573,19 +575,22 @@ int nmpc_fleet_load(nmpc_fleet* f, const int32_t* n_ref, const double* ref, cons
     if (!f) return NMPC_ERR_INVALID;
     nmpc_handle* h = f->h;
     const nmpc_fleet_config& fc = f->fc;
-    if (!n_ref || !ref || !n_vert || (!vert && fc.max_vert > 0) || !start || !goal || !brake_vel || !brake_dist ||
+    const bool have_ref = n_ref && ref;
+    if ((!n_ref != !ref) || !n_vert || (!vert && fc.max_vert > 0) || !start || !goal || !brake_vel || !brake_dist ||
         (fc.n_sched > 0 && (!sched_init || !sched)))
         return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_load: missing array%s", "");
     const size_t B = fc.n_robots, N = h->cfg.N_hor, Nd = h->cfg.Ndynobs;
     for (size_t b = 0; b < B; b++)
-        if (n_ref[b] < 1 || n_ref[b] > fc.max_ref || n_vert[b] < 0 || n_vert[b] > fc.max_vert)
+        if ((have_ref && (n_ref[b] < 1 || n_ref[b] > fc.max_ref)) || n_vert[b] < 0 || n_vert[b] > fc.max_vert)
             return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_load: n_ref / n_vert out of range%s", "");
     CUDA_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     FleetArgs& a = f->a;
 #define UP_(dst, src, n) CUDA_TRY(h, cudaMemcpyAsync((void*)(dst), (src), (n), cudaMemcpyHostToDevice, s))
-    UP_(a.n_ref, n_ref, B * sizeof(int32_t));
-    UP_(a.ref, ref, B * fc.max_ref * 3 * sizeof(double));
+    if (have_ref) {
+        UP_(a.n_ref, n_ref, B * sizeof(int32_t));
+        UP_(a.ref, ref, B * fc.max_ref * 3 * sizeof(double));
+    }
     UP_(a.n_vert, n_vert, B * sizeof(int32_t));
     if (fc.max_vert > 0) UP_(a.vert, vert, B * fc.max_vert * 2 * sizeof(double));
     UP_(a.goal, goal, B * 3 * sizeof(double));
@@ -607,6 +612,51 @@ int nmpc_fleet_load(nmpc_fleet* f, const int32_t* n_ref, const double* ref, cons
     CUDA_TRY(h, cudaMemsetAsync(f->dstatus, 0, B * sizeof(int32_t), s));
     if (a.log) CUDA_TRY(h, cudaMemsetAsync(a.n_logged, 0, B * sizeof(int32_t), s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
+    f->loaded = have_ref;
+    f->staged = true;
+    return NMPC_OK;
+}
+
+int nmpc_fleet_sample_refs(nmpc_fleet* f, const int32_t* n_nodes, const double* nodes, int32_t max_nodes, double v,
+                           double* ref_out, int32_t* n_ref_out) {
+    if (!f) return NMPC_ERR_INVALID;
+    nmpc_handle* h = f->h;
+    if (!f->staged) return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_sample_refs: call nmpc_fleet_load first%s", "");
+    if (!n_nodes || !nodes || max_nodes < 1 || !(v > 0.0)) return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_sample_refs: bad argument%s", "");
+    const nmpc_fleet_config& fc = f->fc;
+    const size_t B = fc.n_robots;
+    for (size_t b = 0; b < B; b++)
+        if (n_nodes[b] < 1 || n_nodes[b] > max_nodes) return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_sample_refs: n_nodes out of range%s", "");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    int32_t* dn = nullptr;
+    double* dnodes = nullptr;
+    CUDA_TRY(h, cudaMalloc(&dn, B * sizeof(int32_t)));
+    cudaError_t e = cudaMalloc(&dnodes, B * max_nodes * 2 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dn, n_nodes, B * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dnodes, nodes, B * max_nodes * 2 * sizeof(double), cudaMemcpyHostToDevice, s);
+    std::vector<int32_t> got(B);
+    if (e == cudaSuccess) {
+        SampleArgs sa;
+        sa.B = (int)B; sa.max_nodes = max_nodes; sa.max_ref = fc.max_ref; sa.v = v; sa.ts = h->cfg.ts;
+        sa.n_nodes = dn; sa.nodes = dnodes; sa.start = f->a.state;
+        sa.ref = (double*)f->a.ref; sa.n_ref = (int32_t*)f->a.n_ref;
+        fleet_sample_refs_kernel<<<((int)B + 127) / 128, 128, 0, s>>>(sa);
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(got.data(), f->a.n_ref, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && ref_out) e = cudaMemcpyAsync(ref_out, f->a.ref, B * fc.max_ref * 3 * sizeof(double), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(dn);
+    cudaFree(dnodes);
+    if (e != cudaSuccess) return set_err(h, NMPC_ERR_CUDA, "nmpc_fleet_sample_refs: %s", cudaGetErrorString(e));
+    for (size_t b = 0; b < B; b++)
+        if (got[b] < 1 || got[b] > fc.max_ref) {
+            f->loaded = false;
+            return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_sample_refs: a reference needs more than max_ref samples%s", "");
+        }
+    if (n_ref_out) memcpy(n_ref_out, got.data(), B * sizeof(int32_t));
     f->loaded = true;
     return NMPC_OK;
 }

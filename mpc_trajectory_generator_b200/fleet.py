@@ -27,7 +27,7 @@ class FleetPlan:
     src/path_generator.py:238-287)."""
 
     def __init__(self, n_ref, ref, n_vert, vert, start, goal, brake_vel, brake_dist, weights, base_speed,
-                 circle_radius, sched_init=None, sched=None):
+                 circle_radius, sched_init=None, sched=None, n_nodes=None, nodes=None, ref_speed=None):
         self.n_ref = np.ascontiguousarray(n_ref, dtype=np.int32)
         self.ref = np.ascontiguousarray(ref, dtype=np.float64)
         self.n_vert = np.ascontiguousarray(n_vert, dtype=np.int32)
@@ -41,6 +41,11 @@ class FleetPlan:
         self.circle_radius = float(circle_radius)
         self.sched_init = None if sched_init is None else np.ascontiguousarray(sched_init, dtype=np.float64)
         self.sched = None if sched is None else np.ascontiguousarray(sched, dtype=np.float64)
+        # waypoints of the global plan (path[1:]) and the sampling speed: only needed to sample the references on
+        # the device (NmpcFleet(..., sample_refs_on_device=True))
+        self.n_nodes = None if n_nodes is None else np.ascontiguousarray(n_nodes, dtype=np.int32)
+        self.nodes = None if nodes is None else np.ascontiguousarray(nodes, dtype=np.float64)
+        self.ref_speed = None if ref_speed is None else float(ref_speed)
         B = self.n_ref.shape[0]
         assert self.ref.shape[0] == B and self.ref.shape[2] == 3 and self.start.shape == (B, 3)
         assert self.goal.shape == (B, 3) and self.n_vert.shape == (B,) and self.vert.shape[0] == B
@@ -74,6 +79,11 @@ class FleetPlan:
                 vert[b, :len(s.vert)] = np.asarray(s.vert, dtype=np.float64)
             start[b] = s.start
             goal[b] = s.end
+        max_nodes = max(len(s.path) - 1 for s in scenarios)
+        n_nodes = np.array([len(s.path) - 1 for s in scenarios], dtype=np.int32)
+        nodes = np.zeros((B, max_nodes, 2))
+        for b, s in enumerate(scenarios):
+            nodes[b, :n_nodes[b]] = np.asarray(s.path[1:], dtype=np.float64)
         sched_init = sched = None
         if len(sc0.dyn_obs):
             if len(sc0.dyn_obs) != Nd:
@@ -93,13 +103,15 @@ class FleetPlan:
                 for k, dob in enumerate(sc0._dyn_obstacles((t + N - 1) * cfg.ts, 1)):
                     sched[m, k, :] = [float(v) for v in dob[0]]
         return cls(n_ref, ref, n_vert, vert, start, goal, sc0.brake_vel, sc0.brake_dist, sc0.weights,
-                   cfg.lin_vel_max * cfg.throttle_ratio, cfg.vehicle_width / 2 + cfg.vehicle_margin, sched_init, sched)
+                   cfg.lin_vel_max * cfg.throttle_ratio, cfg.vehicle_width / 2 + cfg.vehicle_margin, sched_init, sched,
+                   n_nodes=n_nodes, nodes=nodes, ref_speed=cfg.throttle_ratio * 1.1 * cfg.lin_vel_max)
 
 
 class NmpcFleet:
     """B robots stepping in lock-step on one device, bound to an NmpcSolver (its config, device and stream)."""
 
-    def __init__(self, solver, plan, log_steps=0, goal_tol=0.05, stop_tol=0.005):
+    def __init__(self, solver, plan, log_steps=0, goal_tol=0.05, stop_tol=0.005, sample_refs_on_device=False):
+        self.sample_refs_on_device = bool(sample_refs_on_device)
         self.solver = solver
         self.plan = plan
         L = solver._lib
@@ -108,6 +120,7 @@ class NmpcFleet:
         L.nmpc_fleet_create.argtypes = [vp, C.POINTER(FleetConfig), C.POINTER(vp)]
         L.nmpc_fleet_destroy.argtypes = [vp]
         L.nmpc_fleet_load.argtypes = [vp, _ip, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.nmpc_fleet_sample_refs.argtypes = [vp, _ip, _dp, C.c_int32, C.c_double, _dp, _ip]
         L.nmpc_fleet_step.argtypes = [vp, C.c_int32]
         L.nmpc_fleet_state.argtypes = [vp, _dp, _dp, _ip, _ip, _ip, _ip]
         L.nmpc_fleet_last.argtypes = [vp, _dp, _dp, _dp]
@@ -137,9 +150,26 @@ class NmpcFleet:
         """(re)upload the plans and put every robot back at step 0"""
         p = self.plan
         ip = lambda a: a.ctypes.data_as(_ip)  # noqa: E731
-        self._check(self._lib.nmpc_fleet_load(self._f, ip(p.n_ref), _ptr(p.ref), ip(p.n_vert), _ptr(p.vert),
-                                              _ptr(p.start), _ptr(p.goal), _ptr(p.brake_vel), _ptr(p.brake_dist),
-                                              _ptr(p.sched_init), _ptr(p.sched)), "nmpc_fleet_load")
+        dev = self.sample_refs_on_device
+        self._check(self._lib.nmpc_fleet_load(self._f, None if dev else ip(p.n_ref), None if dev else _ptr(p.ref),
+                                              ip(p.n_vert), _ptr(p.vert), _ptr(p.start), _ptr(p.goal),
+                                              _ptr(p.brake_vel), _ptr(p.brake_dist), _ptr(p.sched_init), _ptr(p.sched)),
+                    "nmpc_fleet_load")
+        if dev:
+            self.sample_refs()
+
+    def sample_refs(self, read_back=False):
+        """rough_ref on the device for every robot (plan.nodes / plan.ref_speed); -> (ref, n_ref) if read_back"""
+        p = self.plan
+        if p.nodes is None or p.ref_speed is None:
+            raise NmpcError("the plan carries no waypoints (nodes / n_nodes / ref_speed)")
+        ref = np.zeros((self.B, self.fc.max_ref, 3)) if read_back else None
+        n = np.zeros(self.B, dtype=np.int32) if read_back else None
+        self._check(self._lib.nmpc_fleet_sample_refs(self._f, p.n_nodes.ctypes.data_as(_ip), _ptr(p.nodes),
+                                                     p.nodes.shape[1], p.ref_speed, _ptr(ref),
+                                                     None if n is None else n.ctypes.data_as(_ip)),
+                    "nmpc_fleet_sample_refs")
+        return ref, n
 
     def step(self, n_steps=1):
         self._check(self._lib.nmpc_fleet_step(self._f, int(n_steps)), "nmpc_fleet_step")

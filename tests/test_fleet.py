@@ -153,3 +153,26 @@ def test_fleet_run_to_goal_multi_step_launch(oracle, gpu_solver_factory):
     assert np.array_equal(hist[-1]["state"][0], sa["state"][0])
     fa.close()
     fb.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("complexity", [3, 11])
+def test_device_reference_sampler(gpu_solver_factory, complexity):
+    """rough_ref on the device against the host mirror of src/mpc/mpc_generator.py:17-57.
+    Same statements in the same order; hypot / atan2 are CUDA's instead of glibc's, so the bar is 1e-12 absolute on
+    positions and headings (observed: last-bit differences) and identical sample counts."""
+    import mpc_trajectory_generator_b200 as pkg
+    hc, scs = _scenarios(complexity, 64, seed=30 + complexity)
+    plan = FleetPlan.from_scenarios(scs)
+    solver = gpu_solver_factory(workloads.solver_config_for(hc))
+    fleet = pkg.NmpcFleet(solver, plan, sample_refs_on_device=True)
+    ref, n = fleet.sample_refs(read_back=True)
+    assert np.array_equal(n, plan.n_ref)
+    for b in range(plan.n_robots):
+        assert np.abs(ref[b, :n[b]] - plan.ref[b, :n[b]]).max() <= 1e-12
+    # the fleet steps with the device-made references: first-step parameters agree with the host mirror to 1e-12
+    fleet.step(1)
+    P, _, _ = fleet.last()
+    Ph = np.stack([s.parameters() for s in scs])
+    assert np.abs(P - Ph).max() <= 1e-12
+    fleet.close()
