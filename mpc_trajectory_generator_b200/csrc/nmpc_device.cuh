@@ -102,6 +102,7 @@ enum { H_X0 = 0, H_Y0, H_TH0, H_VINIT, H_WINIT, H_XREF, H_YREF, H_THREF, H_Q, H_
 #define JOB_BYTES 64u
 enum { JOB_EMPTY = 0, JOB_POSTED = 1, JOB_TAKEN = 2, JOB_DONE = 3 };
 #define SEG_STRIDE 6   // s1x s1y | dx dy | inv pad
+#define SEG_PAD 3      // copies of the last segment behind the table: the cross-track loop needs no remainder trips
 #define CIRC_STRIDE 4  // cx cy | r2 (original slot index as int in the 4th double)
 #define ELL_STRIDE 6   // ex ey | cosA sinA | 1/rx^2 1/ry^2
 
@@ -113,7 +114,7 @@ __host__ __device__ inline Lay make_layout(int N, int Nobs, int Nd) {
     Lay L;
     L.n2 = 2 * N;
     int o = V_END * 2 * N;
-    L.seg = o; o += SEG_STRIDE * N;
+    L.seg = o; o += SEG_STRIDE * (N + SEG_PAD + 1);
     L.circ = o; o += CIRC_STRIDE * Nobs;
     L.ell = o; o += ELL_STRIDE * Nd * N;
     L.rho = o; o += 12;
@@ -168,6 +169,20 @@ __device__ __forceinline__ int ldsi(uint32_t a) {
 __device__ __forceinline__ void sts1(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ void sts2(uint32_t a, double2 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+}
+// predicated forms (one instruction each, no branch): active lanes only
+__device__ __forceinline__ double2 lds2_if(uint32_t a, bool on) {
+    double2 v;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+                 "@p ld.shared.v2.f64 {%0, %1}, [%2];\n\t}"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "r"(a), "r"((int)on));
+    return v;
+}
+__device__ __forceinline__ void sts2_if(uint32_t a, double2 v, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p st.shared.v2.f64 [%0], {%1, %2};\n\t}" ::"r"(a), "d"(v.x), "d"(v.y),
+                 "r"((int)on)
+                 : "memory");
 }
 __device__ __forceinline__ void stsi(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
@@ -236,11 +251,9 @@ __device__ __forceinline__ void add_if(double& l, double y, bool on) {
 
 // sincos: Cody-Waite by pi/2 with fma, fdlibm kernel polynomials (same as the oracle)
 __device__ __forceinline__ void nm_sincos(double x, double& s, double& c) {
-    if (!(fabs(x) < 1.0e8)) {
-        s = CUDART_NAN;
-        c = CUDART_NAN;
-        return;
-    }
+    // out-of-range / non-finite arguments give NaN (as in the oracle), without a branch: the reduction runs on 0
+    const bool bad = !(fabs(x) < 1.0e8);
+    x = bad ? 0.0 : x;
     double kf = rint(x * 6.36619772367581382433e-01);
     double r = fma(-kf, 1.57079632679489655800e+00, x);
     r = fma(-kf, 6.12323399573676603587e-17, r);
@@ -264,6 +277,8 @@ __device__ __forceinline__ void nm_sincos(double x, double& s, double& c) {
     double c0 = (q & 1) ? sr : cr;
     s = (q & 2) ? -s0 : s0;
     c = ((q + 1) & 2) ? -c0 : c0;
+    s = bad ? CUDART_NAN : s;
+    c = bad ? CUDART_NAN : c;
 }
 
 // ---------------------------------------------------------------------------------
@@ -517,12 +532,11 @@ struct Warp {
     __device__ __forceinline__ double hdr(int i) const { return lds1(a_hdr + 8u * i); }
     __device__ __forceinline__ void ld(int k, double2 (&r)[P]) const {
 #pragma unroll
-        for (int j = 0; j < P; j++) r[j] = act[j] ? lds2(la[j] + k * vstride) : make_double2(0.0, 0.0);
+        for (int j = 0; j < P; j++) r[j] = lds2_if(la[j] + k * vstride, act[j]);
     }
     __device__ __forceinline__ void st(int k, const double2 (&r)[P]) const {
 #pragma unroll
-        for (int j = 0; j < P; j++)
-            if (act[j]) sts2(la[j] + k * vstride, r[j]);
+        for (int j = 0; j < P; j++) sts2_if(la[j] + k * vstride, r[j], act[j]);
     }
 
     // unpack the parameter row (layout: include/nmpc_b200.h) into the arena
@@ -568,11 +582,13 @@ struct Warp {
             sts2(a + 32u, make_double2(1.0 / (e[2] * e[2]), 1.0 / (e[3] * e[3])));
         }
         const double* pr = pe + 5 * ne;
-        for (int i = lane; i < N; i += 32) {
-            if (i >= 1) {
+        for (int ii = lane; ii < N + SEG_PAD; ii += 32) {
+            if (ii >= 1) {
+                // slots N .. N+SEG_PAD-1 repeat segment N-1: equal distances never win the strict '<' arg-min
+                const int i = (ii < N) ? ii : N - 1;
                 double ax = pr[3 * (i - 1)], ay = pr[3 * (i - 1) + 1];
                 double dx = pr[3 * i] - ax, dy = pr[3 * i + 1] - ay;
-                const uint32_t a = a_seg + 48u * i;
+                const uint32_t a = a_seg + 48u * ii;
                 sts2(a, make_double2(ax, ay));
                 sts2(a + 16u, make_double2(dx, dy));
                 sts1(a + 32u, 1.0 / (fma(dx, dx, dy * dy) + 1e-16));
@@ -676,7 +692,7 @@ struct Warp {
             // UNR segments per trip, written stage by stage: the SM issues in order, so independent
             // chains only overlap if they are interleaved in the instruction stream
             NMPC_NOUNROLL
-            for (; i + UNR <= N; i += UNR, as += 48u * UNR) {
+            for (; i < N; i += UNR, as += 48u * UNR) {
                 double2 s1[UNR], d[UNR];
                 double inv[UNR];
 #pragma unroll
@@ -687,6 +703,7 @@ struct Warp {
                 }
 #pragma unroll
                 for (int j = 0; j < P; j++) {
+                    int iq[UNR];
 #if NMPC_CTE_STAGE
                     double px[UNR], py[UNR], tt[UNR], ex[UNR], ey[UNR], d2[UNR];
 #pragma unroll
@@ -724,20 +741,14 @@ struct Warp {
                     }
 #pragma unroll
 #endif
-                    for (int q = 0; q < UNR; q++) take_if_less(d2[q], i + q, best[j], bi[j]);
-                }
-            }
-            for (; i < N; i++, as += 48u) {
-                const double2 s1 = lds2(as), d = lds2(as + 16u);
-                const double inv = lds1(as + 32u);
+                    for (int q = 0; q < UNR; q++) iq[q] = i + q;
+                    // arg-min of the trip as a tree (the left operand holds the lower indices and wins ties, like the
+                    // serial strict-'<' scan), then ONE merge into the running minimum: the chain between trips is short
 #pragma unroll
-                for (int j = 0; j < P; j++) {
-                    double px = X[j] - s1.x, py = Y[j] - s1.y;
-                    double that = fma(px, d.x, py * d.y) * inv;
-                    double tst = sel_clamp01(that);
-                    double ex = fma(tst, d.x, -px), ey = fma(tst, d.y, -py);
-                    double d2 = fma(ex, ex, ey * ey);
-                    take_if_less(d2, i, best[j], bi[j]);
+                    for (int st = 1; st < UNR; st *= 2)
+#pragma unroll
+                        for (int q = 0; q + st < UNR; q += 2 * st) take_if_less(d2[q + st], iq[q + st], d2[q], iq[q]);
+                    take_if_less(d2[0], iq[0], best[j], bi[j]);
                 }
             }
             }
@@ -1076,7 +1087,22 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
         return (s >= mem1) ? s - mem1 : s;
     };
 
+#ifdef NMPC_PROFILE
+    long long last_t = clock64();
+    int last_slot = -1;  // per-phase cycles outside the evaluations: slots 16+phase (pre), 32+phase (post)
+#define PH_ACCOUNT(next_slot)                                                                                  \
+    do {                                                                                                       \
+        const long long now_ = clock64();                                                                      \
+        if (last_slot >= 0 && prof_out && lane == 0)                                                           \
+            atomicAdd((unsigned long long*)&prof_out[last_slot], (unsigned long long)(now_ - last_t));        \
+        last_t = now_;                                                                                         \
+        last_slot = (next_slot);                                                                               \
+    } while (0)
+#else
+#define PH_ACCOUNT(next_slot) do { } while (0)
+#endif
     for (;;) {
+        PH_ACCOUNT(16 + phase);
         // ------------------------------------------------------------------ pre: pick (x, mode)
         switch (phase) {
             case PH_OUTER_BEGIN: {
@@ -1495,6 +1521,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
         }
 
         // ------------------------------------------------------------------ the one evaluation site
+        PH_ACCOUNT(-1);
         pn_eval = (phase == PH_FINAL) ? make_pen(0.0) : pn;
 #ifdef NMPC_PROFILE
         const long long tp0 = clock64();
@@ -1508,6 +1535,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
 #endif
         if (mode == MODE_GRAD) n_grad++;
         if (mode == MODE_COST && phase != PH_FINAL) n_cost++;
+        PH_ACCOUNT(32 + phase);
 
         // ------------------------------------------------------------------ post
         switch (phase) {

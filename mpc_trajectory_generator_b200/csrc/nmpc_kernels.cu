@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const 
         nmpc_stats st;
         st.cost = 0.0;
 #ifdef NMPC_PROFILE
-        const int status = solve_problem<P, NF>(W, u, yl, st, helper, a_live, nwarps, a.dbg && !helper ? a.dbg + (size_t)b * 16 : nullptr);
+        const int status = solve_problem<P, NF>(W, u, yl, st, helper, a_live, nwarps, a.dbg && !helper ? a.dbg + (size_t)b * 48 : nullptr);
 #else
         const int status = solve_problem<P, NF>(W, u, yl, st, helper, a_live, nwarps);
 #endif

@@ -15,6 +15,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import variants  # noqa: E402
 
+PHASES = ["OUTER_BEGIN", "INIT_A", "INIT_B", "STEP_BEGIN", "LIP", "COST_U", "LIP_LOOP", "LIP_RETRY", "IT0", "LS",
+          "STEP_DONE", "SOLVE_END", "F2", "FINAL", "EXIT", "HELP_WAIT", "HELP_EVAL"]
 SECT = ["theta_scan_sincos", "xy_scan", "cte", "obstacles", "cost_butterfly", "adjoint"]
 
 
@@ -36,7 +38,7 @@ def main():
     s = pkg.NmpcSolver(pkg.NmpcConfig.default(), device=0)
     U, Y, st, stats = s.solve_batch(P2)
     order = np.argsort(-stats["inner_iterations"])
-    dbg = torch.zeros(16, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(48, dtype=torch.int64, device="cuda")
     s._lib.nmpc_debug_set_buffer(C.c_void_p(dbg.data_ptr()))
     for b in list(order[:3]) + [int(order[len(order) // 2])]:
         dbg.zero_()
@@ -50,7 +52,9 @@ def main():
                "lbfgs_calls": int(d[5]), "cycles_per_lbfgs": round(d[4] / max(int(d[5]), 1)),
                "eval_share": round(float(d[0] + d[2]) / d[6], 3), "lbfgs_share": round(float(d[4]) / d[6], 3),
                "sections_cycles_per_eval": {k: round(d[8 + i] / max(ng + nc, 1)) for i, k in enumerate(SECT)},
-               "kernel_ms": s.last_kernel_ms}
+               "kernel_ms": s.last_kernel_ms,
+               "phase_pre_cycles_per_iteration": {PHASES[i]: round(d[16 + i] / max(it, 1)) for i in range(16) if d[16 + i]},
+               "phase_post_cycles_per_iteration": {PHASES[i]: round(d[32 + i] / max(it, 1)) for i in range(16) if d[32 + i]}}
         print(json.dumps(out), flush=True)
     s.close()
 
