@@ -87,10 +87,10 @@ extern __shared__ __align__(16) double smem[];
 #endif
 // Speculative line search on idle warps (experiments/README.md has the measurements): once the problem queue is
 // empty, warps without a problem evaluate the next line-search trials of the warps that still have one.  Bit-exact
-// and 10 % faster for a lone problem, +2..6 % on the B=4096 batch, but the extra ~800 instructions push the hot
-// loop further past the 32 KB instruction cache and cost 2.7 % when every warp owns a problem -> off by default.
+// (who evaluates a trial never changes its bits); on the final round-1 kernel +5 % on the B=4096 batch (the step
+// lasts as long as its hardest problem) and +1 % on a saturated batch.  -DNMPC_HELP_R=0 compiles it out.
 #ifndef NMPC_HELP_R
-#define NMPC_HELP_R 0  // line-search trials a problem may have in flight on idle warps of its CTA (0 = feature off)
+#define NMPC_HELP_R 4  // line-search trials a problem may have in flight on idle warps of its CTA (0 = feature off)
 #endif
 enum { V_GRAD = 0, V_UHALF, V_FPR, V_DIR, V_GSTEP, V_OLDS, V_OLDG, V_S, V_Y = V_S + MEMP1,
        V_U = V_Y + MEMP1, V_YL, V_JG, V_END = V_JG + NMPC_HELP_R };  // V_U, V_YL, V_JG*: what a helper warp reads / writes
