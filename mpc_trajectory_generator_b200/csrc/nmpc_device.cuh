@@ -76,6 +76,12 @@ extern __shared__ __align__(16) double smem[];
 
 // ---------------------------------------------------------------------------------
 // per-warp shared-memory arena (offsets in doubles; every block is 16-byte aligned)
+#ifndef NMPC_HELP_COST
+#define NMPC_HELP_COST 1  // also hand psi(uhalf) (Lipschitz test) to a helper and run the two-loop recursion meanwhile
+#endif
+#ifndef NMPC_HELP_COST_MAXLIVE
+#define NMPC_HELP_COST_MAXLIVE 12
+#endif
 #ifndef NMPC_HELP_EXTRA
 #define NMPC_HELP_EXTRA 9  // trials offered beyond what the previous search needed (9 = always all NMPC_HELP_R)
 #endif
@@ -121,7 +127,7 @@ __host__ __device__ inline Lay make_layout(int N, int Nobs, int Nd) {
     L.alpha = o; o += 12;
     L.hdr = o; o += H_COUNT;
     L.vref = o; o += even_up(N);
-    L.job = o; o += (NMPC_HELP_R > 0 ? NMPC_HELP_R : 1) * (int)(JOB_BYTES / 8);
+    L.job = o; o += (NMPC_HELP_R + 1) * (int)(JOB_BYTES / 8);  // line-search trials + one cost-evaluation record
     L.total = o;
     return L;
 }
@@ -1015,7 +1021,11 @@ enum Phase {
 // x = u - (1-tau) fpr - tau dir, evaluates them in the owner's arena through the same evaluation site and writes
 // back psi, the gradient and the trial's envelope value; it returns when no warp of the CTA owns a problem any
 // more.  Who evaluates a trial never changes its bits, so results do not depend on timing.
-template <int P, int NF>
+// HC (latency mode, chosen by the host for batches that leave warps idle from the start): psi(uhalf) of every
+// iteration is also handed to a helper while the owner runs the L-BFGS update and the two-loop recursion: a lone
+// problem's iteration drops from 29.5k to 23k cycles, but the extra code costs 3-6 % on full batches, hence two
+// instantiations.
+template <int P, int NF, bool HC>
 __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], nmpc_stats& st_out, const bool helper,
                              const uint32_t a_live, const int nwarps, long long* prof_out = nullptr) {
 #ifdef NMPC_PROFILE
@@ -1047,6 +1057,8 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
     bool cont = true, fbe_valid = false;
     double fbe_u = 0.0;
     const double inv_ts = W.hdr(H_INVTS);
+    bool cost_pending = false;  // psi(uhalf) of this iteration is being evaluated by a helper warp
+    bool spec_done = false;     // L-BFGS update and direction of this iteration are already done (speculatively)
     int ls_hint = 0;  // trials the previous line search needed beyond tau = 1
     int ls_seq = 0;   // owner: line searches started (tags job records); helper: slot r of the job being served
 
@@ -1148,6 +1160,39 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 }
                 W.st(V_FPR, fpr);
                 it_lip = 0;
+#if NMPC_HELP_R > 0
+                if constexpr (HC) {
+                // With an idle sub-partition in the CTA, psi(uhalf) (only needed for the Lipschitz test) goes to a
+                // helper warp while this warp already updates the L-BFGS memory and runs the two-loop recursion.
+                // If the test then fails (rare), the update is discarded exactly as the reference discards its memory.
+                // Only in the deep tail (few owners left in the CTA): otherwise the cost jobs take helper time from the
+                // line-search trials of the other owners, which are worth more.
+                if (iteration > 0 && ldv_shared(a_live) <= NMPC_HELP_COST_MAXLIVE &&
+                    __any_sync(FULL, lane < 4 && lane < nwarps && ldv_shared(a_live + 4u + 4u * lane) == 0)) {
+                    const uint32_t aj = W.a_job + JOB_BYTES * NMPC_HELP_R;
+                    int posted = 0;
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int stt = ldv_shared(aj);
+                        if (stt == JOB_EMPTY || stt == JOB_DONE) {
+                            stsi(aj + 4u, 0);  // trial 0 = cost evaluation at uhalf
+                            stsi(aj + 8u, ls_seq);
+                            sts1(aj + 16u, gamma);
+                            sts1(aj + 24u, pn.c);
+                            __threadfence_block();
+                            stv_shared(aj, JOB_POSTED);
+                            posted = 1;
+                        }
+                    }
+                    if (__shfl_sync(FULL, posted, 0)) {
+                        cost_pending = true;
+                        phase = PH_LIP_LOOP;
+                        continue;
+                    }
+                }
+                }
+#endif
 #pragma unroll
                 for (int j = 0; j < P; j++) x[j] = uh[j];
                 mode = MODE_COST;
@@ -1179,12 +1224,16 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                     }
                     hsum4<P>(e0, e1, e2, e3, ip, ys, ss, yy);
                 }
-                const double rhs = cost + LIPSCHITZ_UPDATE_EPSILON * fabs(cost) - ip +
-                                   (GAMMA_L_COEFF * 0.5 * inv_gamma) * (norm_fpr * norm_fpr);
-                if (cost_half > rhs && it_lip < MAX_LIPSCHITZ_UPDATE_ITERATIONS && sget(H_LIP) < MAX_LIPSCHITZ_CONSTANT) {
+                // Lipschitz test of PANOC's step size; on failure: halve gamma, drop the L-BFGS memory, re-evaluate
+                auto lip_test_fails = [&]() -> bool {
+                    const double rhs = cost + LIPSCHITZ_UPDATE_EPSILON * fabs(cost) - ip +
+                                       (GAMMA_L_COEFF * 0.5 * inv_gamma) * (norm_fpr * norm_fpr);
+                    if (!(cost_half > rhs && it_lip < MAX_LIPSCHITZ_UPDATE_ITERATIONS && sget(H_LIP) < MAX_LIPSCHITZ_CONSTANT))
+                        return false;
                     lb_active = 0;
                     lb_first = 1;
                     fbe_valid = false;
+                    spec_done = false;
                     sput(H_LIP, sget(H_LIP) * 2.0);
                     set_gamma(gamma / 2.0);
                     double2 gs[P], uh[P];
@@ -1193,8 +1242,11 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                     for (int j = 0; j < P; j++) x[j] = uh[j];
                     mode = MODE_COST;
                     phase = PH_LIP_RETRY;
-                    break;
-                }
+                    return true;
+                };
+                if (!(HC && cost_pending) && lip_test_fails()) break;
+                double2 q[P];
+                if (!(HC && spec_done)) {
                 // lbfgs_direction(): update_hessian(g = fpr, state = u)
                 if (lb_first) {
                     lb_first = 0;
@@ -1233,7 +1285,6 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
 #ifdef NMPC_PROFILE
                 const long long tl0 = clock64();
 #endif
-                double2 q[P];
 #pragma unroll
                 for (int j = 0; j < P; j++) q[j] = fpr[j];
 #if NMPC_LB_PREFETCH
@@ -1329,6 +1380,39 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
 #ifdef NMPC_PROFILE
                 prof[4] += clock64() - tl0;
                 prof[5]++;
+#endif
+                } else {  // update and direction were done before psi(uhalf) was known
+                    W.ld(V_DIR, q);
+                    spec_done = false;
+                }
+#if NMPC_HELP_R > 0
+                if constexpr (HC) if (cost_pending) {
+                    cost_pending = false;
+                    const uint32_t aj = W.a_job + JOB_BYTES * NMPC_HELP_R;
+                    int got = 0;
+                    if (lane == 0) {
+                        int stt = ldv_shared(aj);
+                        if (stt == JOB_POSTED && cas_shared(aj, JOB_POSTED, JOB_EMPTY) == JOB_POSTED) stt = JOB_EMPTY;
+                        if (stt != JOB_EMPTY) {
+                            while (ldv_shared(aj) != JOB_DONE) __nanosleep(20);
+                            got = 1;
+                        }
+                    }
+                    got = __shfl_sync(FULL, got, 0);
+                    if (!got) {  // no helper picked it up: evaluate here and come back (update / direction are kept)
+                        spec_done = true;
+                        W.ld(V_UHALF, x);
+                        mode = MODE_COST;
+                        phase = PH_LIP;
+                        break;
+                    }
+                    __threadfence_block();
+                    cost_half = lds1(aj + 32u);
+                    n_cost += 2;  // the evaluation and OpEn's re-evaluation of psi(u) (see PH_LIP)
+                    __syncwarp();
+                    if (lane == 0) stv_shared(aj, JOB_EMPTY);
+                    if (lip_test_fails()) break;
+                }
 #endif
                 // linesearch(): right-hand side on the forward-backward envelope
                 if (fbe_valid) {
@@ -1426,7 +1510,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
             case PH_HELP_WAIT: {
                 // poll the job records of every warp of the CTA: lane l looks at record (r, o) = (l / nwarps, l % nwarps),
                 // so the lowest set bit of the vote is the most urgent trial (smallest r) on offer
-                const int njobs = nwarps * NMPC_HELP_R;
+                const int njobs = nwarps * (NMPC_HELP_R + 1);
                 int j = -1;
                 const uint32_t a_part = a_live + 4u + 4u * ((threadIdx.x >> 5) & 3u);  // this warp's sub-partition
                 for (;;) {
@@ -1476,6 +1560,13 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 set_gamma(lds1(aj + 16u));
                 pn = make_pen(lds1(aj + 24u));
                 ls_seq = r;
+                W.ld(V_YL, yl);
+                if (trial == 0) {  // psi(uhalf) for the owner's Lipschitz test
+                    W.ld(V_UHALF, x);
+                    mode = MODE_COST;
+                    phase = PH_HELP_EVAL;
+                    break;
+                }
                 tau = 1.0;
                 for (int k = 0; k < trial; k++) tau /= 2.0;
                 const double om = 1.0 - tau;
@@ -1483,7 +1574,6 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 W.ld(V_U, uo);
                 W.ld(V_FPR, fpr);
                 W.ld(V_DIR, dir);
-                W.ld(V_YL, yl);
 #pragma unroll
                 for (int jj = 0; jj < P; jj++) {
                     x[jj].x = fma(-tau, dir[jj].x, fma(-om, fpr[jj].x, uo[jj].x));
@@ -1701,6 +1791,15 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
             }
 #if NMPC_HELP_R > 0
             case PH_HELP_EVAL: {  // helper: envelope value of the trial, results into the owner's arena
+                if (mode == MODE_COST) {
+                    const uint32_t ajc = W.a_job + JOB_BYTES * ls_seq;
+                    if (lane == 0) sts1(ajc + 32u, psi);
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) stv_shared(ajc, JOB_DONE);
+                    phase = PH_HELP_WAIT;
+                    break;
+                }
                 double e[P], f[P], d2, gg;
 #pragma unroll
                 for (int j = 0; j < P; j++) {

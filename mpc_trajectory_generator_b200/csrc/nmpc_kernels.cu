@@ -22,7 +22,7 @@
 // N=80/Nobs=200), so fewer warps fit anyway: cap the CTA accordingly and let ptxas use the registers.
 __host__ __device__ constexpr int warps_cap(int P) { return P == 1 ? NMPC_WARPS : (P == 2 ? 8 : 5); }
 
-template <int P, int NF>
+template <int P, int NF, bool HC>
 __global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const __grid_constant__ KArgs a) {
     const nmpc_config& cfg = a.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const 
     __shared__ int cta_live[5];
     const uint32_t a_live = (uint32_t)__cvta_generic_to_shared(&cta_live[0]);
     if (threadIdx.x < 5) cta_live[threadIdx.x] = (threadIdx.x == 0) ? nwarps : (nwarps - (int)threadIdx.x + 1 + 3) / 4;
-    if (lane < (NMPC_HELP_R > 0 ? NMPC_HELP_R : 1)) stsi(W.a_job + JOB_BYTES * lane, JOB_EMPTY);
+    if (lane < NMPC_HELP_R + 1) stsi(W.a_job + JOB_BYTES * lane, JOB_EMPTY);
     __syncthreads();
     bool helper = false;
     for (;;) {
@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const 
         nmpc_stats st;
         st.cost = 0.0;
 #ifdef NMPC_PROFILE
-        const int status = solve_problem<P, NF>(W, u, yl, st, helper, a_live, nwarps, a.dbg && !helper ? a.dbg + (size_t)b * 48 : nullptr);
+        const int status = solve_problem<P, NF, HC>(W, u, yl, st, helper, a_live, nwarps, a.dbg && !helper ? a.dbg + (size_t)b * 48 : nullptr);
 #else
-        const int status = solve_problem<P, NF>(W, u, yl, st, helper, a_live, nwarps);
+        const int status = solve_problem<P, NF, HC>(W, u, yl, st, helper, a_live, nwarps);
 #endif
         if (helper) break;  // no warp of the CTA owns a problem any more
 #pragma unroll
@@ -212,17 +212,25 @@ const char* nmpc_last_error(nmpc_handle* h) { return h ? h->err : "null handle";
 // Optional compile-time-N instantiation (fully unrolled cross-track loop with a tree arg-min).  Measured on
 // B200 (round 1, tools/variants.py): a lone warp's evaluation gets 15 % faster, but the larger hot loop costs
 // more in instruction fetch than it saves (config 2: 45.6k vs 48.6k solves/s), so it is off by default.
+// 0: never use the latency instantiation, 1: always, 2: for batches up to half the machine's warp slots
+#ifndef NMPC_LATENCY_MODE
+#define NMPC_LATENCY_MODE 2
+#endif
 #ifndef NMPC_FIXED_N
 #define NMPC_FIXED_N 0
 #endif
-static const void* solve_kernel_for(int N) {
+// latency = true: the instantiation that also overlaps psi(uhalf) with the two-loop recursion (solve_problem<HC>)
+static const void* solve_kernel_for(int N, bool latency) {
 #if NMPC_FIXED_N > 0
-    if (N == NMPC_FIXED_N) return (const void*)nmpc_solve_kernel<(NMPC_FIXED_N + 31) / 32, NMPC_FIXED_N>;
+    if (N == NMPC_FIXED_N)
+        return latency ? (const void*)nmpc_solve_kernel<(NMPC_FIXED_N + 31) / 32, NMPC_FIXED_N, true>
+                       : (const void*)nmpc_solve_kernel<(NMPC_FIXED_N + 31) / 32, NMPC_FIXED_N, false>;
 #endif
+    const bool lat = latency && NMPC_HELP_R > 0 && NMPC_HELP_COST;
     switch ((N + 31) / 32) {
-        case 1: return (const void*)nmpc_solve_kernel<1, 0>;
-        case 2: return (const void*)nmpc_solve_kernel<2, 0>;
-        default: return (const void*)nmpc_solve_kernel<3, 0>;
+        case 1: return lat ? (const void*)nmpc_solve_kernel<1, 0, true> : (const void*)nmpc_solve_kernel<1, 0, false>;
+        case 2: return lat ? (const void*)nmpc_solve_kernel<2, 0, true> : (const void*)nmpc_solve_kernel<2, 0, false>;
+        default: return lat ? (const void*)nmpc_solve_kernel<3, 0, true> : (const void*)nmpc_solve_kernel<3, 0, false>;
     }
 }
 static const void* eval_kernel_for(int N) {
@@ -274,7 +282,9 @@ int nmpc_create(const nmpc_config* cfg, int device, nmpc_handle** out) {
     if (w > warps_cap(h->P)) w = warps_cap(h->P);
     h->warps_per_cta = w;
     h->smem_bytes = per_warp * w;
-    e = cudaFuncSetAttribute(solve_kernel_for(h->cfg.N_hor), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    e = cudaFuncSetAttribute(solve_kernel_for(h->cfg.N_hor, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(solve_kernel_for(h->cfg.N_hor, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(eval_kernel_for(h->cfg.N_hor), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -343,7 +353,11 @@ static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU,
     if (grid > ctas_needed) grid = ctas_needed;
     if (grid < 1) grid = 1;
     void* args[] = {&a};
-    CUDA_TRY(h, cudaLaunchKernel(solve_kernel_for(h->cfg.N_hor), dim3(grid), dim3(32 * h->warps_per_cta), args, h->smem_bytes, s));
+    // batches that cannot fill the machine (every problem gets a warp at once and warps sit idle from the start) run
+    // the latency instantiation; full batches the plain one
+    const bool latency = (NMPC_LATENCY_MODE == 1) || (NMPC_LATENCY_MODE == 2 && B <= h->sm_count * h->warps_per_cta / 2);
+    CUDA_TRY(h, cudaLaunchKernel(solve_kernel_for(h->cfg.N_hor, latency), dim3(grid), dim3(32 * h->warps_per_cta), args,
+                                 h->smem_bytes, s));
     h->launches++;
     return NMPC_OK;
 }
