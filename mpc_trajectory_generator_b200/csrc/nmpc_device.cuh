@@ -23,12 +23,6 @@
 #include "../../include/nmpc_b200.h"
 
 #define FULL 0xffffffffu
-#ifndef NMPC_OBS_QUICK
-#define NMPC_OBS_QUICK 0
-#endif
-#ifndef NMPC_CTE_STAGE
-#define NMPC_CTE_STAGE 0
-#endif
 // Code size matters as much as instruction count here: the per-iteration hot loop of the solver is about the
 // size of the SM's 32 KB L1.5 instruction cache, and a loop that no longer fits misses on every line (measured:
 // a lone warp's two-loop recursion slows from 5.7k to 7.9k cycles when the evaluation code grows by 15 %).
@@ -49,9 +43,6 @@
 #define NMPC_STAGES _Pragma("unroll")
 #else
 #define NMPC_STAGES _Pragma("unroll 1")
-#endif
-#ifndef NMPC_LB_PREFETCH
-#define NMPC_LB_PREFETCH 1
 #endif
 #ifndef NMPC_ICLAMP
 #define NMPC_ICLAMP 0  // measured neutral on B200 (round 1); the compare-select form is the oracle's
@@ -84,9 +75,6 @@ extern __shared__ __align__(16) double smem[];
 #endif
 #ifndef NMPC_HELP_EXTRA
 #define NMPC_HELP_EXTRA 9  // trials offered beyond what the previous search needed (9 = always all NMPC_HELP_R)
-#endif
-#ifndef NMPC_HELP_MODE
-#define NMPC_HELP_MODE 0
 #endif
 #ifndef NMPC_HELP_SLEEP
 #define NMPC_HELP_SLEEP 100  // ns between two polls of an idle helper
@@ -710,32 +698,6 @@ struct Warp {
 #pragma unroll
                 for (int j = 0; j < P; j++) {
                     int iq[UNR];
-#if NMPC_CTE_STAGE
-                    double px[UNR], py[UNR], tt[UNR], ex[UNR], ey[UNR], d2[UNR];
-#pragma unroll
-                    for (int q = 0; q < UNR; q++) {
-                        px[q] = X[j] - s1[q].x;
-                        py[q] = Y[j] - s1[q].y;
-                    }
-#pragma unroll
-                    for (int q = 0; q < UNR; q++) tt[q] = py[q] * d[q].y;
-#pragma unroll
-                    for (int q = 0; q < UNR; q++) tt[q] = fma(px[q], d[q].x, tt[q]);
-#pragma unroll
-                    for (int q = 0; q < UNR; q++) tt[q] = tt[q] * inv[q];
-#pragma unroll
-                    for (int q = 0; q < UNR; q++) tt[q] = sel_clamp01(tt[q]);
-#pragma unroll
-                    for (int q = 0; q < UNR; q++) {
-                        ex[q] = fma(tt[q], d[q].x, -px[q]);
-                        ey[q] = fma(tt[q], d[q].y, -py[q]);
-                    }
-#pragma unroll
-                    for (int q = 0; q < UNR; q++) d2[q] = ey[q] * ey[q];
-#pragma unroll
-                    for (int q = 0; q < UNR; q++) d2[q] = fma(ex[q], ex[q], d2[q]);
-#pragma unroll
-#else
                     double d2[UNR];
 #pragma unroll
                     for (int q = 0; q < UNR; q++) {
@@ -746,7 +708,6 @@ struct Warp {
                         d2[q] = fma(ex, ex, ey * ey);
                     }
 #pragma unroll
-#endif
                     for (int q = 0; q < UNR; q++) iq[q] = i + q;
                     // arg-min of the trip as a tree (the left operand holds the lower indices and wins ties, like the
                     // serial strict-'<' scan), then ONE merge into the running minimum: the chain between trips is short
@@ -1287,7 +1248,6 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
 #endif
 #pragma unroll
                 for (int j = 0; j < P; j++) q[j] = fpr[j];
-#if NMPC_LB_PREFETCH
                 if (lb_active > 0) {
                     // each step's (s, y) pair is fetched while the previous step's butterfly is in flight
                     double2 sv[P], yv[P], sn[P], yn[P];
@@ -1338,44 +1298,6 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                         rho = rho_n;
                     }
                 }
-#else
-                if (lb_active > 0) {
-                    NMPC_NOUNROLL
-                    for (int k = 0; k < lb_active; k++) {
-                        const int sl = slot(k);
-                        double2 sv[P], yv[P];
-                        W.ld(V_S + sl, sv);
-                        W.ld(V_Y + sl, yv);
-                        const double al = lds1(W.a_rho + 8u * sl) * wdot<P>(sv, q);
-                        if (lane == 0) sts1(W.a_alpha + 8u * k, al);
-#pragma unroll
-                        for (int j = 0; j < P; j++) {
-                            q[j].x = fma(-al, yv[j].x, q[j].x);
-                            q[j].y = fma(-al, yv[j].y, q[j].y);
-                        }
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        q[j].x = q[j].x * lb_gamma;
-                        q[j].y = q[j].y * lb_gamma;
-                    }
-                    NMPC_NOUNROLL
-                    for (int k = lb_active - 1; k >= 0; k--) {
-                        const int sl = slot(k);
-                        double2 sv[P], yv[P];
-                        W.ld(V_S + sl, sv);
-                        W.ld(V_Y + sl, yv);
-                        const double beta = lds1(W.a_rho + 8u * sl) * wdot<P>(yv, q);
-                        const double co = lds1(W.a_alpha + 8u * k) - beta;
-#pragma unroll
-                        for (int j = 0; j < P; j++) {
-                            q[j].x = fma(co, sv[j].x, q[j].x);
-                            q[j].y = fma(co, sv[j].y, q[j].y);
-                        }
-                    }
-                }
-#endif
                 W.st(V_DIR, q);
 #ifdef NMPC_PROFILE
                 prof[4] += clock64() - tl0;
@@ -1516,15 +1438,9 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 for (;;) {
                     if (ldv_shared(a_live) <= 0) return 0;
                     if (ldv_shared(a_part) > 0) {  // an owner shares this sub-partition: stay out of its way
-#if NMPC_HELP_MODE >= 1
-                        return 0;
-#endif
                         __nanosleep(2000);
                         continue;
                     }
-#if NMPC_HELP_MODE >= 2
-                    if ((threadIdx.x >> 5) >= 4) return 0;
-#endif
                     unsigned m = 0;
                     int base = 0;
                     for (; base < njobs && !m; base += 32) {

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const 
                     add_shared(a_live + 4u + 4u * (warp & 3), -1);
                     add_shared(a_live, -1);
                 }
-                if (NMPC_HELP_R == 0 || nwarps == 1 || NMPC_HELP_MODE == 3) break;
+                if (NMPC_HELP_R == 0 || nwarps == 1) break;
                 helper = true;
             } else if (a.skip && a.skip[b]) {
                 continue;
