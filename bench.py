@@ -342,7 +342,8 @@ def main():
                        "parity": "bit-exact vs oracle/ (tests/test_gpu_parity.py); OpEn itself not runnable here"},
             "ms_per_solve": total_ms_max / args.steps / B,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
-                    "ms_per_step": e2e_ms_step, "api": "NmpcSolver.solve_batch_into -> nmpc_solve_batch (C ABI), pinned host buffers"},
+                    "ms_per_step": e2e_ms_step, "api": "NmpcSolver.solve_batch_into -> nmpc_solve_batch (C ABI) on pinned host buffers; the kernel reads "
+                           "the inputs from and writes the results to those buffers over PCIe in place (each byte once)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(args.workload, B), "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",

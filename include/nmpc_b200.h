@@ -140,7 +140,9 @@ int nmpc_call(nmpc_handle* h, const double* p, double* u_out, int32_t* exit_stat
 /* forget the persisted warm start of nmpc_call (a freshly started server) */
 int nmpc_reset_warm_start(nmpc_handle* h);
 
-/* Batched solve, HOST buffers (copies inside the call).
+/* Batched solve, HOST buffers.  Pageable buffers are staged through device scratch (copies inside the call);
+ * page-locked buffers (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are read and written by the kernel
+ * in place over PCIe — every row moves exactly once either way.
  *   P  [B, np]  row-major parameters
  *   U  [B, 2N]  in: initial guess, out: solution (the projected half step, always inside U)
  *   Y  [B, 2N]  in: initial multipliers, out: multiplier state a server would keep; nullable (zeros)

@@ -1373,8 +1373,8 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                     W.st(V_U, u);
                     __threadfence_block();
                     __syncwarp();
-                    // offer as many trials as the previous search needed plus one: a search that accepts tau = 1
-                    // leaves nothing running behind it (late helpers slow the owner's shuffles down)
+                    // NMPC_HELP_EXTRA < NMPC_HELP_R would limit the offer to what the previous search needed plus
+                    // EXTRA trials (less speculative work); measured worse than always offering all of them
                     if (lane < NMPC_HELP_R && lane < ls_hint + NMPC_HELP_EXTRA) {
                         const uint32_t aj = W.a_job + JOB_BYTES * lane;
                         const int stt = ldv_shared(aj);

@@ -216,6 +216,9 @@ const char* nmpc_last_error(nmpc_handle* h) { return h ? h->err : "null handle";
 #ifndef NMPC_LATENCY_MODE
 #define NMPC_LATENCY_MODE 2
 #endif
+#ifndef NMPC_ZEROCOPY
+#define NMPC_ZEROCOPY 1  // nmpc_solve_batch on page-locked host buffers: no staging copies
+#endif
 #ifndef NMPC_FIXED_N
 #define NMPC_FIXED_N 0
 #endif
@@ -384,11 +387,44 @@ static int ensure_scratch(nmpc_handle* h, int B) {
     return NMPC_OK;
 }
 
+// device-visible alias of a page-locked host buffer (cudaHostAlloc / cudaHostRegister / torch pin_memory), or NULL
+static void* pinned_alias(const void* p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return (at.type == cudaMemoryTypeHost) ? at.devicePointer : nullptr;
+}
+
 int nmpc_solve_batch(nmpc_handle* h, int32_t B, const double* P, double* U, double* Y, int32_t* status,
                      nmpc_stats* stats) {
     if (!h || B < 0 || !P || !U) return set_err(h, NMPC_ERR_INVALID, "nmpc_solve_batch: bad argument%s", "");
     if (B == 0) return NMPC_OK;
     CUDA_TRY(h, cudaSetDevice(h->device));
+    {
+        // Page-locked caller buffers are read and written by the kernel in place: every row is touched once per
+        // solve (3.4 KB in, 0.7 KB out against ~10 ms of arithmetic), so the PCIe latency hides behind the other
+        // warps and no staging copy sits in front of the kernel.
+        void* aP = pinned_alias(P);
+        void* aU = pinned_alias(U);
+        void* aY = Y ? pinned_alias(Y) : nullptr;
+        void* aS = status ? pinned_alias(status) : nullptr;
+        void* aT = stats ? pinned_alias(stats) : nullptr;
+        if (NMPC_ZEROCOPY && aP && aU && (!Y || aY) && (!status || aS) && (!stats || aT) && Y) {
+            cudaStream_t s = h->stream;
+            CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+            int rc0 = launch_solve(h, B, (const double*)aP, (double*)aU, (double*)aY, (int32_t*)aS, (nmpc_stats*)aT, s);
+            if (rc0) return rc0;
+            CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+            CUDA_TRY(h, cudaStreamSynchronize(s));
+            float ms0 = 0.f;
+            CUDA_TRY(h, cudaEventElapsedTime(&ms0, h->ev0, h->ev1));
+            h->last_ms = ms0;
+            return NMPC_OK;
+        }
+    }
     int rc = ensure_scratch(h, B);
     if (rc) return rc;
     const size_t n2 = 2 * (size_t)h->cfg.N_hor;

@@ -238,6 +238,24 @@ def test_small_batches_with_idle_warps(oracle, gpu_solver_factory, N, Nobs, B):
             assert np.array_equal(stats[k], statso[k]), k
 
 
+def test_pinned_host_buffers_in_place(gpu_solver_factory):
+    """nmpc_solve_batch on page-locked buffers (the kernel reads / writes them in place) == the staged-copy path."""
+    import torch
+    import mpc_trajectory_generator_b200 as pkg
+    g = pkg.NmpcConfig.default()
+    B = 300
+    P = problems.synth(20, 10, 3, B, seed=77, active=True)
+    s = gpu_solver_factory(g)
+    U, Y, st, stats = s.solve_batch(P)                      # pageable numpy arrays: staged copies
+    hP = torch.from_numpy(P).pin_memory()
+    hU = torch.zeros((B, 40), dtype=torch.float64).pin_memory()
+    hY = torch.zeros((B, 40), dtype=torch.float64).pin_memory()
+    hst = torch.zeros(B, dtype=torch.int32).pin_memory()
+    s.solve_batch_into(hP.numpy(), hU.numpy(), hY.numpy(), hst.numpy(), None)
+    assert np.array_equal(hU.numpy(), U) and np.array_equal(hY.numpy(), Y) and np.array_equal(hst.numpy(), st)
+    assert s.last_kernel_ms > 0
+
+
 def test_device_pointer_entry(oracle, gpu_solver_factory):
     """nmpc_solve_batch_device on torch tensors / torch's current stream (the path bench.py times)."""
     import torch
