@@ -70,6 +70,9 @@ extern __shared__ __align__(16) double smem[];
 #ifndef NMPC_HELP_COST
 #define NMPC_HELP_COST 1  // also hand psi(uhalf) (Lipschitz test) to a helper and run the two-loop recursion meanwhile
 #endif
+#ifndef NMPC_HELP_PART_MAX
+#define NMPC_HELP_PART_MAX 0  // helpers work from SM sub-partitions with at most this many owners
+#endif
 #ifndef NMPC_HELP_COST_MAXLIVE
 #define NMPC_HELP_COST_MAXLIVE 12
 #endif
@@ -982,7 +985,7 @@ enum Phase {
 // x = u - (1-tau) fpr - tau dir, evaluates them in the owner's arena through the same evaluation site and writes
 // back psi, the gradient and the trial's envelope value; it returns when no warp of the CTA owns a problem any
 // more.  Who evaluates a trial never changes its bits, so results do not depend on timing.
-// HC (latency mode, chosen by the host for batches that leave warps idle from the start): psi(uhalf) of every
+// HC (latency mode, chosen by the host for batches of at most two problems per SM): psi(uhalf) of every
 // iteration is also handed to a helper while the owner runs the L-BFGS update and the two-loop recursion: a lone
 // problem's iteration drops from 29.5k to 23k cycles, but the extra code costs 3-6 % on full batches, hence two
 // instantiations.
@@ -1129,7 +1132,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 // Only in the deep tail (few owners left in the CTA): otherwise the cost jobs take helper time from the
                 // line-search trials of the other owners, which are worth more.
                 if (iteration > 0 && ldv_shared(a_live) <= NMPC_HELP_COST_MAXLIVE &&
-                    __any_sync(FULL, lane < 4 && lane < nwarps && ldv_shared(a_live + 4u + 4u * lane) == 0)) {
+                    __any_sync(FULL, lane < 4 && lane < nwarps && ldv_shared(a_live + 4u + 4u * lane) <= NMPC_HELP_PART_MAX)) {
                     const uint32_t aj = W.a_job + JOB_BYTES * NMPC_HELP_R;
                     int posted = 0;
                     __threadfence_block();
@@ -1366,7 +1369,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 // a_live[0]: warps of the CTA in owner mode; a_live[1..4]: the same per SM sub-partition (warp % 4).
                 // Helpers only work from a sub-partition without owners, so they never take issue slots or FP64
                 // pipe cycles from a warp that is solving a problem.
-                const bool idle_part = __any_sync(FULL, lane < 4 && lane < nwarps && ldv_shared(a_live + 4u + 4u * lane) == 0);
+                const bool idle_part = __any_sync(FULL, lane < 4 && lane < nwarps && ldv_shared(a_live + 4u + 4u * lane) <= NMPC_HELP_PART_MAX);
                 if (idle_part) {
                     // offer the next trials (tau = 1/2, 1/4, ...) while this warp evaluates tau = 1.
                     // A record still held by a late helper of an earlier search is skipped.
@@ -1437,7 +1440,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 const uint32_t a_part = a_live + 4u + 4u * ((threadIdx.x >> 5) & 3u);  // this warp's sub-partition
                 for (;;) {
                     if (ldv_shared(a_live) <= 0) return 0;
-                    if (ldv_shared(a_part) > 0) {  // an owner shares this sub-partition: stay out of its way
+                    if (ldv_shared(a_part) > NMPC_HELP_PART_MAX) {  // owners share this sub-partition: stay out of their way
                         __nanosleep(2000);
                         continue;
                     }

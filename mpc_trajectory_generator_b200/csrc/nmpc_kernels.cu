@@ -36,12 +36,20 @@ __global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const 
     if (threadIdx.x < 5) cta_live[threadIdx.x] = (threadIdx.x == 0) ? nwarps : (nwarps - (int)threadIdx.x + 1 + 3) / 4;
     if (lane < NMPC_HELP_R + 1) stsi(W.a_job + JOB_BYTES * lane, JOB_EMPTY);
     __syncthreads();
-    bool helper = false;
+    // First wave: warp w of CTA c takes problem c + gridDim.x * w, so a batch smaller than the machine is spread
+    // over the SMs (one or two owners per SM, the other warps help) instead of filling a few CTAs; afterwards the
+    // problems come from the atomic queue.
+    bool helper = false, first = true;
     for (;;) {
         int b = 0;
         if (!helper) {
-            if (lane == 0) b = (int)atomicAdd(a.counter, 1u);
-            b = __shfl_sync(FULL, b, 0);
+            if (first) {
+                b = (int)(blockIdx.x + gridDim.x * warp);
+                first = false;
+            } else {
+                if (lane == 0) b = (int)(gridDim.x * nwarps + atomicAdd(a.counter, 1u));
+                b = __shfl_sync(FULL, b, 0);
+            }
             if (b >= a.B) {  // queue empty: this warp will not own a problem again
                 if (lane == 0) {
                     add_shared(a_live + 4u + 4u * (warp & 3), -1);
@@ -212,7 +220,7 @@ const char* nmpc_last_error(nmpc_handle* h) { return h ? h->err : "null handle";
 // Optional compile-time-N instantiation (fully unrolled cross-track loop with a tree arg-min).  Measured on
 // B200 (round 1, tools/variants.py): a lone warp's evaluation gets 15 % faster, but the larger hot loop costs
 // more in instruction fetch than it saves (config 2: 45.6k vs 48.6k solves/s), so it is off by default.
-// 0: never use the latency instantiation, 1: always, 2: for batches up to half the machine's warp slots
+// 0: never use the latency instantiation, 1: always, 2: for batches of at most two problems per SM
 #ifndef NMPC_LATENCY_MODE
 #define NMPC_LATENCY_MODE 2
 #endif
@@ -350,15 +358,13 @@ static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU,
     a.dbg = g_dbg;
 #endif
     CUDA_TRY(h, cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), s));
-    const int warps_needed = B;
-    int grid = h->sm_count;
-    const int ctas_needed = (warps_needed + h->warps_per_cta - 1) / h->warps_per_cta;
-    if (grid > ctas_needed) grid = ctas_needed;
+    int grid = h->sm_count;  // one persistent CTA per SM; fewer only if there are fewer problems than SMs
+    if (grid > B) grid = B;
     if (grid < 1) grid = 1;
     void* args[] = {&a};
-    // batches that cannot fill the machine (every problem gets a warp at once and warps sit idle from the start) run
-    // the latency instantiation; full batches the plain one
-    const bool latency = (NMPC_LATENCY_MODE == 1) || (NMPC_LATENCY_MODE == 2 && B <= h->sm_count * h->warps_per_cta / 2);
+    // batches of at most two problems per SM (SM sub-partitions stay free for helper warps from the start) run the
+    // latency instantiation; larger ones the plain one (measured crossover between B = 296 and 592 on 148 SMs)
+    const bool latency = (NMPC_LATENCY_MODE == 1) || (NMPC_LATENCY_MODE == 2 && B <= 2 * h->sm_count);
     CUDA_TRY(h, cudaLaunchKernel(solve_kernel_for(h->cfg.N_hor, latency), dim3(grid), dim3(32 * h->warps_per_cta), args,
                                  h->smem_bytes, s));
     h->launches++;
