@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) fleet_assemble_kernel(const __grid_consta
     const double x = f.state[3 * b], y = f.state[3 * b + 1], th = f.state[3 * b + 2];
     const double lv = f.last_u[2 * b], lw = f.last_u[2 * b + 1];
     const double* __restrict__ goal = f.goal + 3 * (size_t)b;
-    const double gx = goal[0], gy = goal[1], gth = goal[2];
+    const double gx = goal[0], gy = goal[1];
     const int t = f.t[b];
 
     // ---- reference index: closest sample inside [idx-1, idx+5) (src/path_generator.py:330-333)
