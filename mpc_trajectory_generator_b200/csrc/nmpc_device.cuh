@@ -1131,7 +1131,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 // If the test then fails (rare), the update is discarded exactly as the reference discards its memory.
                 // Only in the deep tail (few owners left in the CTA): otherwise the cost jobs take helper time from the
                 // line-search trials of the other owners, which are worth more.
-                if (iteration > 0 && ldv_shared(a_live) <= NMPC_HELP_COST_MAXLIVE &&
+                if (__builtin_expect(iteration > 0 && ldv_shared(a_live) <= NMPC_HELP_COST_MAXLIVE, 0) &&
                     __any_sync(FULL, lane < 4 && lane < nwarps && ldv_shared(a_live + 4u + 4u * lane) <= NMPC_HELP_PART_MAX)) {
                     const uint32_t aj = W.a_job + JOB_BYTES * NMPC_HELP_R;
                     int posted = 0;
@@ -1208,9 +1208,9 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                     phase = PH_LIP_RETRY;
                     return true;
                 };
-                if (!(HC && cost_pending) && lip_test_fails()) break;
+                if (!(HC && __builtin_expect(cost_pending, 0)) && lip_test_fails()) break;
                 double2 q[P];
-                if (!(HC && spec_done)) {
+                if (!(HC && __builtin_expect(spec_done, 0))) {
                 // lbfgs_direction(): update_hessian(g = fpr, state = u)
                 if (lb_first) {
                     lb_first = 0;
@@ -1311,7 +1311,7 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                     spec_done = false;
                 }
 #if NMPC_HELP_R > 0
-                if constexpr (HC) if (cost_pending) {
+                if constexpr (HC) if (__builtin_expect(cost_pending, 0)) {
                     cost_pending = false;
                     const uint32_t aj = W.a_job + JOB_BYTES * NMPC_HELP_R;
                     int got = 0;

@@ -364,7 +364,7 @@ static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU,
     void* args[] = {&a};
     // batches of at most two problems per SM (SM sub-partitions stay free for helper warps from the start) run the
     // latency instantiation; larger ones the plain one (measured crossover between B = 296 and 592 on 148 SMs)
-    const bool latency = (NMPC_LATENCY_MODE == 1) || (NMPC_LATENCY_MODE == 2 && B <= 2 * h->sm_count);
+    const bool latency = (NMPC_LATENCY_MODE == 1) || (NMPC_LATENCY_MODE == 2 && B <= 2 * h->sm_count);  // 3: see HC_TAIL
     CUDA_TRY(h, cudaLaunchKernel(solve_kernel_for(h->cfg.N_hor, latency), dim3(grid), dim3(32 * h->warps_per_cta), args,
                                  h->smem_bytes, s));
     h->launches++;
