@@ -172,7 +172,8 @@ int nmpc_eval_batch(nmpc_handle* h, int32_t B, const double* P, const double* U,
  *             reference's solver process keeps between mng.call()s (src/mpc/mpc_generator.py:206),
  *   advance   apply the first control, integrate the plant (src/mpc/mpc_generator.py:223-235) and
  *             run the termination test (src/path_generator.py:397).
- * n steps are enqueued back to back on the handle's stream without a host round trip.
+ * n steps are enqueued back to back on the handle's stream without a host round trip.  Fleets larger than the GPU's
+ * warp slots are solved longest-first (by each robot's iteration count in the previous step): scheduling only.
  * Restrictions (documented deviations): num_steps_taken = 1 (configs/default.yaml:17); a map has either
  * no dynamic obstacles (phantom unit discs, src/path_generator.py:274-280) or exactly Ndynobs of them.
  */

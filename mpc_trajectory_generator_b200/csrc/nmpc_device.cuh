@@ -133,6 +133,7 @@ struct KArgs {
     nmpc_stats* stats;
     unsigned int* counter;
     const int32_t* skip;  // nullable: rows with skip[b] != 0 are left untouched (fleet: robots that have terminated)
+    const int32_t* order; // nullable: permutation of 0..B-1, the order in which problems are handed out
     // eval kernel only
     const double* cvec;
     double *psi, *grad, *F1, *F2;

@@ -288,3 +288,41 @@ __global__ void __launch_bounds__(128) fleet_sample_refs_kernel(const __grid_con
     }
     a.n_ref[b] = n;
 }
+
+// Longest-first order for the next step's solve (scheduling only, results do not depend on it): a robot's inner
+// iteration count of the previous step predicts the next one's, and starting the long solves first shortens the tail
+// of a fleet larger than the machine's warp slots.  Counting sort over 256 buckets of 20 iterations, descending.
+struct OrderArgs {
+    int B;
+    const nmpc_stats* stats;
+    const int32_t* done;
+    int32_t* hist;    // [256], zeroed by the caller
+    int32_t* order;   // [B]
+};
+__device__ __forceinline__ int order_bucket(const OrderArgs& a, int b) {
+    if (a.done[b]) return 255;
+    const int it = a.stats[b].inner_iterations;
+    const int k = it / 20;
+    return 254 - (k > 254 ? 254 : k);
+}
+__global__ void __launch_bounds__(256) fleet_order_hist_kernel(const __grid_constant__ OrderArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < a.B) atomicAdd(&a.hist[order_bucket(a, b)], 1);
+}
+__global__ void __launch_bounds__(256) fleet_order_scan_kernel(const __grid_constant__ OrderArgs a) {
+    __shared__ int sh[256];
+    const int t = threadIdx.x;
+    sh[t] = a.hist[t];
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+        const int v = (t >= off) ? sh[t - off] : 0;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    a.hist[t] = sh[t] - a.hist[t];  // exclusive prefix: first slot of the bucket
+}
+__global__ void __launch_bounds__(256) fleet_order_scatter_kernel(const __grid_constant__ OrderArgs a) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < a.B) a.order[atomicAdd(&a.hist[order_bucket(a, b)], 1)] = b;
+}

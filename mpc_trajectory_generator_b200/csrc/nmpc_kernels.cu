@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const 
                 if (lane == 0) b = (int)(gridDim.x * nwarps + atomicAdd(a.counter, 1u));
                 b = __shfl_sync(FULL, b, 0);
             }
+            if (b < a.B && a.order) b = a.order[b];
             if (b >= a.B) {  // queue empty: this warp will not own a problem again
                 if (lane == 0) {
                     add_shared(a_live + 4u + 4u * (warp & 3), -1);
@@ -224,6 +225,9 @@ const char* nmpc_last_error(nmpc_handle* h) { return h ? h->err : "null handle";
 #ifndef NMPC_LATENCY_MODE
 #define NMPC_LATENCY_MODE 2
 #endif
+#ifndef NMPC_FLEET_ORDER
+#define NMPC_FLEET_ORDER 1  // fleets: longest-first order from the previous step's iteration counts
+#endif
 #ifndef NMPC_ZEROCOPY
 #define NMPC_ZEROCOPY 1  // nmpc_solve_batch on page-locked host buffers: no staging copies
 #endif
@@ -341,7 +345,7 @@ int nmpc_ping(nmpc_handle* h) {
 }
 
 static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU, double* dY, int32_t* dstatus,
-                        nmpc_stats* dstats, cudaStream_t s, const int32_t* dskip = nullptr) {
+                        nmpc_stats* dstats, cudaStream_t s, const int32_t* dskip = nullptr, const int32_t* dorder = nullptr) {
     KArgs a;
     memset(&a, 0, sizeof(a));
     a.cfg = h->cfg;
@@ -354,6 +358,7 @@ static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU,
     a.stats = dstats;
     a.counter = h->counter;
     a.skip = dskip;
+    a.order = dorder;
 #ifdef NMPC_PROFILE
     a.dbg = g_dbg;
 #endif
@@ -548,6 +553,8 @@ struct nmpc_fleet {
     nmpc_stats* dstats;
     double *dU, *dY;
     int32_t* dstatus;
+    int32_t *dorder, *dhist;  // longest-first order of the next solve (fleet_order_* kernels)
+    bool have_order;
     bool loaded;  // plans complete (references uploaded or sampled)
     bool staged;  // nmpc_fleet_load has run
 };
@@ -594,6 +601,8 @@ int nmpc_fleet_create(nmpc_handle* h, const nmpc_fleet_config* fc, nmpc_fleet** 
     TRY_(dalloc(&f->dY, B * 2 * N));
     TRY_(dalloc(&f->dstatus, B));
     TRY_(dalloc(&f->dstats, B));
+    TRY_(dalloc(&f->dorder, B));
+    TRY_(dalloc(&f->dhist, (size_t)256));
     if (fc->log_steps > 0) {
         TRY_(dalloc(&a.log, B * fc->log_steps * 5));
         TRY_(dalloc(&a.n_logged, B));
@@ -621,6 +630,7 @@ int nmpc_fleet_destroy(nmpc_fleet* f) {
     cudaFree(a.state); cudaFree(a.last_u); cudaFree(a.t); cudaFree(a.idx); cudaFree(a.done); cudaFree(a.P);
     cudaFree(a.log); cudaFree(a.n_logged);
     cudaFree(f->dU); cudaFree(f->dY); cudaFree(f->dstatus); cudaFree(f->dstats);
+    cudaFree(f->dorder); cudaFree(f->dhist);
     delete f;
     return NMPC_OK;
 }
@@ -670,6 +680,7 @@ int nmpc_fleet_load(nmpc_fleet* f, const int32_t* n_ref, const double* ref, cons
     CUDA_TRY(h, cudaStreamSynchronize(s));
     f->loaded = have_ref;
     f->staged = true;
+    f->have_order = false;
     return NMPC_OK;
 }
 
@@ -728,10 +739,22 @@ int nmpc_fleet_step(nmpc_fleet* f, int32_t n_steps) {
     for (int k = 0; k < n_steps; k++) {
         fleet_assemble_kernel<<<(B * 32 + 255) / 256, 256, 0, s>>>(f->a);
         h->launches++;
-        int rc = launch_solve(h, B, f->a.P, f->dU, f->dY, f->dstatus, f->dstats, s, f->a.done);
+        // fleets larger than the machine's warp slots: hand the robots out longest-first (by the previous step)
+        const bool use_order = NMPC_FLEET_ORDER && f->have_order && B > h->sm_count * h->warps_per_cta;
+        int rc = launch_solve(h, B, f->a.P, f->dU, f->dY, f->dstatus, f->dstats, s, f->a.done, use_order ? f->dorder : nullptr);
         if (rc) return rc;
         fleet_advance_kernel<<<(B + 255) / 256, 256, 0, s>>>(f->a);
         h->launches++;
+        if (NMPC_FLEET_ORDER && B > h->sm_count * h->warps_per_cta) {
+            OrderArgs oa;
+            oa.B = B; oa.stats = f->dstats; oa.done = f->a.done; oa.hist = f->dhist; oa.order = f->dorder;
+            CUDA_TRY(h, cudaMemsetAsync(f->dhist, 0, 256 * sizeof(int32_t), s));
+            fleet_order_hist_kernel<<<(B + 255) / 256, 256, 0, s>>>(oa);
+            fleet_order_scan_kernel<<<1, 256, 0, s>>>(oa);
+            fleet_order_scatter_kernel<<<(B + 255) / 256, 256, 0, s>>>(oa);
+            h->launches += 3;
+            f->have_order = true;
+        }
     }
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
     CUDA_TRY(h, cudaGetLastError());
