@@ -23,6 +23,7 @@
 #include "../../include/nmpc_b200.h"
 
 #define FULL 0xffffffffu
+#define PROBE_BUCKETS 1024
 // Code size matters as much as instruction count here: the per-iteration hot loop of the solver is about the
 // size of the SM's 32 KB L1.5 instruction cache, and a loop that no longer fits misses on every line (measured:
 // a lone warp's two-loop recursion slows from 5.7k to 7.9k cycles when the evaluation code grows by 15 %).
@@ -134,6 +135,8 @@ struct KArgs {
     unsigned int* counter;
     const int32_t* skip;  // nullable: rows with skip[b] != 0 are left untouched (fleet: robots that have terminated)
     const int32_t* order; // nullable: permutation of 0..B-1, the order in which problems are handed out
+    int32_t* probe_bucket; // probe kernel: sort bucket of every problem
+    int32_t* probe_hist;   // probe kernel: bucket histogram (PROBE_BUCKETS ints)
     // eval kernel only
     const double* cvec;
     double *psi, *grad, *F1, *F2;

@@ -103,6 +103,71 @@ __global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const 
     }
 }
 
+// Probe for the longest-first schedule: |grad psi(u0)|^2 of every problem — ONE evaluation, 1/3700 of an average
+// solve — ranks the problems by the work they will need (Spearman 0.82 with the inner-iteration count on the
+// BASELINE config-2 batch; tools/ and DESIGN.md §5).  The kernel writes a sort bucket per problem (exponent and three
+// mantissa bits of the squared norm, descending) and the bucket histogram; two tiny kernels turn that into the order
+// in which the solve kernel hands the problems out.  Scheduling only: results do not depend on it.
+template <int P, int NF>
+__global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_probe_kernel(const __grid_constant__ KArgs a) {
+    const nmpc_config& cfg = a.cfg;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Lay L = make_layout(cfg.N_hor, cfg.Nobs, cfg.Ndynobs);
+    const int N = NF ? NF : cfg.N_hor;
+    const int wpb = blockDim.x >> 5;
+    Warp<P, NF> W(cfg, L, warp, lane);
+    const Pen pn = make_pen(cfg.initial_penalty);
+    for (int b = blockIdx.x * wpb + warp; b < a.B; b += gridDim.x * wpb) {
+        int bucket = PROBE_BUCKETS - 1;  // skipped rows go last
+        if (!(a.skip && a.skip[b])) {
+            W.stage(a.P + (size_t)b * a.np);
+            double2 u[P], yl[P], g[P];
+            const double* U0 = a.U + (size_t)b * 2 * N;
+            const double* Y0 = a.Y ? a.Y + (size_t)b * 2 * N : nullptr;
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                const int t = lane + 32 * j;
+                u[j] = (t < N) ? *reinterpret_cast<const double2*>(U0 + 2 * t) : make_double2(0.0, 0.0);
+                yl[j] = (t < N && Y0) ? make_double2(Y0[t], Y0[N + t]) : make_double2(0.0, 0.0);
+            }
+            double pen;
+            W.eval(MODE_GRAD, u, pn, yl, g, pen, nullptr);
+            double e[P];
+#pragma unroll
+            for (int j = 0; j < P; j++) e[j] = fma(g[j].y, g[j].y, g[j].x * g[j].x);
+            const double k = hsum<P>(e);
+            // exponent + 3 mantissa bits, window 2^-64 .. 2^64; NaN / inf count as hardest
+            const int hi = (int)((unsigned long long)__double_as_longlong(k) >> 49) & 0x7fff;
+            int idx = hi - ((1023 - 64) << 3);
+            idx = idx < 0 ? 0 : (idx > PROBE_BUCKETS - 2 ? PROBE_BUCKETS - 2 : idx);
+            bucket = PROBE_BUCKETS - 2 - idx;
+        }
+        if (lane == 0) {
+            a.probe_bucket[b] = bucket;
+            atomicAdd(&a.probe_hist[bucket], 1);
+        }
+        __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(PROBE_BUCKETS) order_scan_kernel(int32_t* hist) {
+    __shared__ int sh[PROBE_BUCKETS];
+    const int t = threadIdx.x;
+    const int own = hist[t];
+    sh[t] = own;
+    __syncthreads();
+    for (int off = 1; off < PROBE_BUCKETS; off <<= 1) {
+        const int v = (t >= off) ? sh[t - off] : 0;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    hist[t] = sh[t] - own;  // exclusive prefix: first slot of the bucket
+}
+__global__ void __launch_bounds__(256) order_scatter_kernel(const int32_t* bucket, int32_t* hist, int32_t* order, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) order[atomicAdd(&hist[bucket[b]], 1)] = b;
+}
+
 // parity hook: psi, grad, F1, F2 for B (p, u, c, y) tuples
 template <int P, int NF>
 __global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_eval_kernel(const __grid_constant__ KArgs a) {
@@ -164,6 +229,9 @@ struct nmpc_handle {
     int32_t* dstatus;
     nmpc_stats* dstats;
     int cap;
+    // longest-first schedule of large batches (probe + counting sort)
+    int32_t *pbucket, *porder, *phist;
+    int pcap;
     // nmpc_call state (what OpEn's TCP server keeps between requests)
     double *call_u, *call_y;
     int64_t launches;
@@ -225,6 +293,9 @@ const char* nmpc_last_error(nmpc_handle* h) { return h ? h->err : "null handle";
 #ifndef NMPC_LATENCY_MODE
 #define NMPC_LATENCY_MODE 2
 #endif
+#ifndef NMPC_AUTO_ORDER
+#define NMPC_AUTO_ORDER 1  // batches larger than the warp slots: probe + longest-first order before the solve
+#endif
 #ifndef NMPC_FLEET_ORDER
 #define NMPC_FLEET_ORDER 1  // fleets: longest-first order from the previous step's iteration counts
 #endif
@@ -246,6 +317,13 @@ static const void* solve_kernel_for(int N, bool latency) {
         case 1: return lat ? (const void*)nmpc_solve_kernel<1, 0, true> : (const void*)nmpc_solve_kernel<1, 0, false>;
         case 2: return lat ? (const void*)nmpc_solve_kernel<2, 0, true> : (const void*)nmpc_solve_kernel<2, 0, false>;
         default: return lat ? (const void*)nmpc_solve_kernel<3, 0, true> : (const void*)nmpc_solve_kernel<3, 0, false>;
+    }
+}
+static const void* probe_kernel_for(int N) {
+    switch ((N + 31) / 32) {
+        case 1: return (const void*)nmpc_probe_kernel<1, 0>;
+        case 2: return (const void*)nmpc_probe_kernel<2, 0>;
+        default: return (const void*)nmpc_probe_kernel<3, 0>;
     }
 }
 static const void* eval_kernel_for(int N) {
@@ -302,6 +380,8 @@ int nmpc_create(const nmpc_config* cfg, int device, nmpc_handle** out) {
         e = cudaFuncSetAttribute(solve_kernel_for(h->cfg.N_hor, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(eval_kernel_for(h->cfg.N_hor), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(probe_kernel_for(h->cfg.N_hor), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&h->counter, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&h->call_u, 2 * cfg->N_hor * sizeof(double));
@@ -323,6 +403,7 @@ int nmpc_destroy(nmpc_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->counter);
+    cudaFree(h->pbucket); cudaFree(h->porder); cudaFree(h->phist);
     cudaFree(h->call_u);
     cudaFree(h->call_y);
     cudaFree(h->dP);
@@ -359,6 +440,28 @@ static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU,
     a.counter = h->counter;
     a.skip = dskip;
     a.order = dorder;
+    if (NMPC_AUTO_ORDER && !dorder && B > h->sm_count * h->warps_per_cta) {
+        // more problems than warp slots: rank them with one gradient evaluation each and start the long ones first
+        if (B > h->pcap) {
+            cudaFree(h->pbucket); cudaFree(h->porder); cudaFree(h->phist);
+            h->pbucket = h->porder = h->phist = nullptr; h->pcap = 0;
+            CUDA_TRY(h, cudaMalloc(&h->pbucket, (size_t)B * sizeof(int32_t)));
+            CUDA_TRY(h, cudaMalloc(&h->porder, (size_t)B * sizeof(int32_t)));
+            CUDA_TRY(h, cudaMalloc(&h->phist, PROBE_BUCKETS * sizeof(int32_t)));
+            h->pcap = B;
+        }
+        a.probe_bucket = h->pbucket;
+        a.probe_hist = h->phist;
+        CUDA_TRY(h, cudaMemsetAsync(h->phist, 0, PROBE_BUCKETS * sizeof(int32_t), s));
+        int pgrid = (B + h->warps_per_cta - 1) / h->warps_per_cta;
+        if (pgrid > h->sm_count) pgrid = h->sm_count;
+        void* pargs[] = {&a};
+        CUDA_TRY(h, cudaLaunchKernel(probe_kernel_for(h->cfg.N_hor), dim3(pgrid), dim3(32 * h->warps_per_cta), pargs, h->smem_bytes, s));
+        order_scan_kernel<<<1, PROBE_BUCKETS, 0, s>>>(h->phist);
+        order_scatter_kernel<<<(B + 255) / 256, 256, 0, s>>>(h->pbucket, h->phist, h->porder, B);
+        h->launches += 3;
+        a.order = h->porder;
+    }
 #ifdef NMPC_PROFILE
     a.dbg = g_dbg;
 #endif
