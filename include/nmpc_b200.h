@@ -150,6 +150,10 @@ int nmpc_reset_warm_start(nmpc_handle* h);
 int nmpc_solve_batch(nmpc_handle* h, int32_t B, const double* P, double* U, double* Y,
                      int32_t* status, nmpc_stats* stats);
 
+/* Scheduling note for all batched entry points: a batch with more problems than the GPU has warp slots (148 SMs x 12)
+ * is first ranked by one gradient evaluation per problem (|grad psi(u0)| predicts the iteration count) and handed to
+ * the persistent warps longest-first; smaller batches are spread over the SMs.  Results never depend on the order. */
+
 /* Batched solve, DEVICE buffers on the handle's device, asynchronous on `stream`
  * (a cudaStream_t passed as void*; NULL = CUDA's default stream, as for any cudaStream_t).
  * Same arrays as nmpc_solve_batch; the caller orders its own copies on that stream. */
