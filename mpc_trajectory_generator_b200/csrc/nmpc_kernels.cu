@@ -293,6 +293,9 @@ const char* nmpc_last_error(nmpc_handle* h) { return h ? h->err : "null handle";
 #ifndef NMPC_LATENCY_MODE
 #define NMPC_LATENCY_MODE 2
 #endif
+#ifndef NMPC_AUTO_ORDER_ALL
+#define NMPC_AUTO_ORDER_ALL 0  // 1: also order batches that fit the warp slots (spreads the long solves over the SMs)
+#endif
 #ifndef NMPC_AUTO_ORDER
 #define NMPC_AUTO_ORDER 1  // batches larger than the warp slots: probe + longest-first order before the solve
 #endif
@@ -440,7 +443,7 @@ static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU,
     a.counter = h->counter;
     a.skip = dskip;
     a.order = dorder;
-    if (NMPC_AUTO_ORDER && !dorder && B > h->sm_count * h->warps_per_cta) {
+    if (NMPC_AUTO_ORDER && !dorder && B > (NMPC_AUTO_ORDER_ALL ? 2 * h->sm_count : h->sm_count * h->warps_per_cta)) {
         // more problems than warp slots: rank them with one gradient evaluation each and start the long ones first
         if (B > h->pcap) {
             cudaFree(h->pbucket); cudaFree(h->porder); cudaFree(h->phist);
