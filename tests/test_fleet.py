@@ -176,3 +176,30 @@ def test_device_reference_sampler(gpu_solver_factory, complexity):
     Ph = np.stack([s.parameters() for s in scs])
     assert np.abs(P - Ph).max() <= 1e-12
     fleet.close()
+
+
+@pytest.mark.gpu
+def test_large_fleet_longest_first_order(oracle, gpu_solver_factory):
+    """A fleet larger than the GPU's warp slots: steps after the first hand the robots to the solve kernel longest-first
+    (device counting sort on the previous step's iteration counts), the first one by the probe.  Scheduling must not
+    change anything: every replica of a scenario follows its host loop bit for bit."""
+    import mpc_trajectory_generator_b200 as pkg
+    hc, scs = _scenarios(3, 16, seed=77)
+    plan = FleetPlan.from_scenarios(scs)
+    rep = 130                                   # 16 x 130 = 2080 robots > 148 SMs x 12 warps
+    tile = lambda a: np.ascontiguousarray(np.concatenate([a] * rep))  # noqa: E731
+    big = FleetPlan(tile(plan.n_ref), tile(plan.ref), tile(plan.n_vert), tile(plan.vert), tile(plan.start),
+                    tile(plan.goal), plan.brake_vel, plan.brake_dist, plan.weights, plan.base_speed, plan.circle_radius)
+    solver = gpu_solver_factory(workloads.solver_config_for(hc))
+    fleet = pkg.NmpcFleet(solver, big)
+    steps = 4
+    hist = _host_loop(oracle, hc, scs, steps, lambda th: oracle.sincos(th))
+    fleet.step(steps)
+    P, U, Y = fleet.last()
+    st = fleet.state()
+    for r in range(rep):
+        sl = slice(16 * r, 16 * (r + 1))
+        assert np.array_equal(U[sl], hist[-1]["U"]) and np.array_equal(Y[sl], hist[-1]["Y"])
+        assert np.array_equal(st["state"][sl], hist[-1]["state"]) and np.array_equal(P[sl], hist[-1]["P"])
+        assert np.array_equal(st["status"][sl], hist[-1]["status"])
+    fleet.close()
