@@ -67,7 +67,7 @@ enum {
 enum {
     NMPC_CONVERGED = 0,              /* "Converged"                     */
     NMPC_NOT_CONVERGED_ITERATIONS = 1, /* "NotConvergedIterations"      */
-    NMPC_NOT_CONVERGED_OUT_OF_TIME = 2, /* "NotConvergedOutOfTime" (only if a cycle budget is set) */
+    NMPC_NOT_CONVERGED_OUT_OF_TIME = 2, /* "NotConvergedOutOfTime" (only with nmpc_config.max_duration_micros > 0) */
     NMPC_NOT_FINITE = 3              /* solver error 2000 in the reference's TCP reply:
                                         is_ok() == False (src/mpc/mpc_generator.py:215-221) */
 };
@@ -83,7 +83,10 @@ typedef struct nmpc_config {
     int32_t lbfgs_memory;         /* 10 */
     int32_t max_inner_iterations; /* 500 */
     int32_t max_outer_iterations; /* 10 */
-    int32_t reserved0, reserved1;
+    int32_t max_duration_micros;  /* 0 = no time limit (default: results stay deterministic).  > 0: OpEn's
+                                     with_max_duration_micros (src/mpc/mpc_generator.py:9,186: 500 000): the solve
+                                     ends with NotConvergedOutOfTime once that much device time has passed */
+    int32_t reserved1;
     double ts;                    /* configs/default.yaml:18 */
     double lin_vel_min, lin_vel_max, ang_vel_max; /* set U, src/mpc/mpc_generator.py:151-153 */
     double lin_acc_min, lin_acc_max, ang_acc_max; /* set C, src/mpc/mpc_generator.py:164-168 */

@@ -24,11 +24,17 @@ def find_nvcc():
     return None
 
 
+def sources():
+    """Every file the library is compiled from (csrc/*.cu, csrc/*.cuh and the public header)."""
+    import glob
+    return sorted(glob.glob(os.path.join(_HERE, "csrc", "*.cu*"))) + [HDR]
+
+
 def is_stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(f) > t for f in (SRC, DEV, HDR))
+    return any(os.path.getmtime(f) > t for f in sources())
 
 
 def build_library(force=False, verbose=False):
@@ -43,7 +49,14 @@ def build_variant(out, defines=(), verbose=False):
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libnmpc_b200.so")
+    # compile next to the target and rename: a concurrent loader (other torchrun ranks) never sees a partial file
+    tmp = f"{out}.tmp.{os.getpid()}"
     cmd = ([nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
-           + ["-o", out, SRC])
-    subprocess.check_call(cmd)
+           + ["-o", tmp, SRC])
+    try:
+        subprocess.check_call(cmd)
+        os.replace(tmp, out)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
     return out

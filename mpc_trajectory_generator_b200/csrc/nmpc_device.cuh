@@ -1,20 +1,31 @@
-// nmpc_device.cuh — device code of the batched NMPC solver (one warp per problem).
+// nmpc_device.cuh — device code of the batched NMPC solver (one warp per problem, G-lane evaluation groups).
 //
 // What it computes is the problem of MpcModule.build() (src/mpc/mpc_generator.py:66-193) solved
 // the way the reference's OpEn solver does (PANOC + L-BFGS inside an ALM/penalty loop); the
-// control flow mirrors oracle/nmpc_oracle.c step by step and the arithmetic follows the contract
-// in DESIGN.md §4 (explicit fma, own sincos, warp-ordered reductions), so results are bit-identical
-// to the oracle.
+// results are those of oracle/nmpc_oracle.c bit for bit (same statements, same arithmetic contract,
+// explicit fma, own sincos, group-ordered reductions).
 //
-// Organisation:
-//   * lane l owns horizon steps t = l + 32*j (P = ceil(N/32) register passes);
-//   * rollout and adjoint sweep are Kogge-Stone scans over lanes; reductions are xor-butterflies;
-//   * the per-problem constants (segments, circles, ellipses, weights) and the PANOC / L-BFGS
-//     vectors live in the warp's shared-memory arena, addressed with explicit 32-bit shared
-//     addresses (ld.shared / st.shared) so no generic-address arithmetic is left in the loops;
-//   * the solver is a phase machine with ONE evaluation site: every psi / grad psi / F2
-//     evaluation of PANOC, the line search, the Lipschitz backtracking and the ALM update goes
-//     through the same code, which keeps the kernel small enough for the instruction caches.
+// Organisation (round 2):
+//   * a warp owns one problem.  Its 32 lanes form NG = 32 / G evaluation groups of G lanes (G = 8 for
+//     N <= 24, else 16); inside a group lane i owns the S consecutive horizon steps S*i .. S*i+S-1, so
+//     every per-step quantity is S independent dependency chains per lane (the latency-bound FP64 code
+//     gets its instruction-level parallelism from there) and every reduction / scan over the horizon is
+//     S-1 serial adds plus log2(G) shuffle stages;
+//   * the PANOC / L-BFGS vector algebra is replicated in every group (same loads, same results), the
+//     EVALUATIONS are not: one call of eval() computes psi and grad psi at NG different points at once,
+//     one per group.  PANOC's iteration needs psi(u_half) (Lipschitz test) and then psi, grad psi at the
+//     line-search trials tau = 1, 1/2, 1/4, ... one after the other; here the L-BFGS update and the
+//     two-loop recursion run first (they do not need psi(u_half)) and ONE call evaluates u_half and the
+//     first NG-1 trials together.  76 % of the iterations of the BASELINE config-2 batch end with that
+//     single call (3.4 sequential evaluations per iteration in round 1).  The speculation is exact: a
+//     trial's value does not depend on who evaluates it or when, the Lipschitz test that fails (rare)
+//     discards the L-BFGS update exactly like the reference discards its memory, and the evaluation
+//     counters report what the reference's serial loop would have evaluated;
+//   * the per-problem constants and the PANOC / L-BFGS vectors live in the warp's shared-memory arena
+//     (vector element (s, i) at 16*(G*s + i): a group's lanes read 16*G contiguous bytes, conflict-free),
+//     addressed with explicit 32-bit shared addresses;
+//   * the solver is a phase machine with ONE evaluation site, which keeps the hot loop near the size of
+//     the instruction cache.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -24,31 +35,10 @@
 
 #define FULL 0xffffffffu
 #define PROBE_BUCKETS 1024
-// Code size matters as much as instruction count here: the per-iteration hot loop of the solver is about the
-// size of the SM's 32 KB L1.5 instruction cache, and a loop that no longer fits misses on every line (measured:
-// a lone warp's two-loop recursion slows from 5.7k to 7.9k cycles when the evaluation code grows by 15 %).
-// NMPC_UNROLL_LOOPS=1 lets ptxas unroll the latency-bound loops again (tools/variants.py).
-#ifndef NMPC_UNROLL_LOOPS
-#define NMPC_UNROLL_LOOPS 0
-#endif
-#if NMPC_UNROLL_LOOPS
-#define NMPC_NOUNROLL
-#else
-#define NMPC_NOUNROLL _Pragma("unroll 1")
-#endif
-// the five exchange stages of every warp reduction / scan: unrolled (1) or a real loop (0, smaller code)
-#ifndef NMPC_STAGE_UNROLL
-#define NMPC_STAGE_UNROLL 1
-#endif
-#if NMPC_STAGE_UNROLL
-#define NMPC_STAGES _Pragma("unroll")
-#else
-#define NMPC_STAGES _Pragma("unroll 1")
-#endif
-#ifndef NMPC_ICLAMP
-#define NMPC_ICLAMP 0  // measured neutral on B200 (round 1); the compare-select form is the oracle's
-#endif
 #define MEMP1 (NMPC_LBFGS_MAX + 1)
+#ifndef NMPC_SEG_UNR
+#define NMPC_SEG_UNR 2  // reference segments per trip of the cross-track loop (x S steps per lane in flight)
+#endif
 
 // OpEn PANOC constants (panoc_engine.rs) — see oracle/nmpc_oracle.c for the restatement notes
 #define MIN_L_ESTIMATE 1e-10
@@ -67,59 +57,45 @@
 extern __shared__ __align__(16) double smem[];
 
 // ---------------------------------------------------------------------------------
+// horizon layout: G lanes per evaluation group, S consecutive steps per lane (same rule as nmpc_oracle_layout)
+__host__ __device__ inline void nmpc_layout_for(int N, int& G, int& S) {
+    if (N <= 16) { G = 8; S = 2; }
+    else if (N <= 24) { G = 8; S = 3; }
+    else if (N <= 32) { G = 16; S = 2; }
+    else if (N <= 48) { G = 16; S = 3; }
+    else if (N <= 64) { G = 16; S = 4; }
+    else { G = 16; S = 6; }
+}
+
 // per-warp shared-memory arena (offsets in doubles; every block is 16-byte aligned)
-#ifndef NMPC_HELP_COST
-#define NMPC_HELP_COST 1  // also hand psi(uhalf) (Lipschitz test) to a helper and run the two-loop recursion meanwhile
-#endif
-#ifndef NMPC_HELP_PART_MAX
-#define NMPC_HELP_PART_MAX 0  // helpers work from SM sub-partitions with at most this many owners
-#endif
-#ifndef NMPC_HELP_COST_MAXLIVE
-#define NMPC_HELP_COST_MAXLIVE 12
-#endif
-#ifndef NMPC_HELP_EXTRA
-#define NMPC_HELP_EXTRA 9  // trials offered beyond what the previous search needed (9 = always all NMPC_HELP_R)
-#endif
-#ifndef NMPC_HELP_SLEEP
-#define NMPC_HELP_SLEEP 100  // ns between two polls of an idle helper
-#endif
-// Speculative line search on idle warps (experiments/README.md has the measurements): once the problem queue is
-// empty, warps without a problem evaluate the next line-search trials of the warps that still have one.  Bit-exact
-// (who evaluates a trial never changes its bits); on the final round-1 kernel +5 % on the B=4096 batch (the step
-// lasts as long as its hardest problem) and +1 % on a saturated batch.  -DNMPC_HELP_R=0 compiles it out.
-#ifndef NMPC_HELP_R
-#define NMPC_HELP_R 4  // line-search trials a problem may have in flight on idle warps of its CTA (0 = feature off)
-#endif
-enum { V_GRAD = 0, V_UHALF, V_FPR, V_DIR, V_GSTEP, V_OLDS, V_OLDG, V_S, V_Y = V_S + MEMP1,
-       V_U = V_Y + MEMP1, V_YL, V_JG, V_END = V_JG + NMPC_HELP_R };  // V_U, V_YL, V_JG*: what a helper warp reads / writes
+enum { V_GRAD = 0, V_UHALF, V_FPR, V_DIR, V_GSTEP, V_OLDS, V_OLDG, V_U, V_YL, V_T0, V_S, V_Y = V_S + MEMP1,
+       V_END = V_Y + MEMP1 };
 enum { H_X0 = 0, H_Y0, H_TH0, H_VINIT, H_WINIT, H_XREF, H_YREF, H_THREF, H_Q, H_QV, H_QTH, H_RV, H_RW, H_QN, H_QTHN,
        H_QCTE, H_AP, H_WP, H_INVTS,
        // warp-uniform solver state that is touched once per outer iteration (kept out of the registers)
        H_F2N, H_DYN, H_F2NP, H_DYNP, H_NORMH, H_LIP, H_AKKT, H_NCIRC /* int */, H_COUNT = 28 };
-// job record of one speculative line-search trial (bytes): state, trial, seq (ints) | gamma | c | psi | lhs
-#define JOB_BYTES 64u
-enum { JOB_EMPTY = 0, JOB_POSTED = 1, JOB_TAKEN = 2, JOB_DONE = 3 };
 #define SEG_STRIDE 6   // s1x s1y | dx dy | inv pad
-#define SEG_PAD 3      // copies of the last segment behind the table: the cross-track loop needs no remainder trips
 #define CIRC_STRIDE 4  // cx cy | r2 (original slot index as int in the 4th double)
 #define ELL_STRIDE 6   // ex ey | cosA sinA | 1/rx^2 1/ry^2
 
 struct Lay {
-    int n2, seg, circ, ell, rho, alpha, hdr, vref, job, total;
+    int vlen, seg, circ, ell, ebd, rho, alpha, hdr, vref, total;
 };
 __host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
 __host__ __device__ inline Lay make_layout(int N, int Nobs, int Nd) {
+    int G, S;
+    nmpc_layout_for(N, G, S);
     Lay L;
-    L.n2 = 2 * N;
-    int o = V_END * 2 * N;
-    L.seg = o; o += SEG_STRIDE * (N + SEG_PAD + 1);
-    L.circ = o; o += CIRC_STRIDE * Nobs;
+    L.vlen = 2 * G * S;  // doubles per vector: (v, w) for G*S step slots, slots >= N stay zero
+    int o = V_END * L.vlen;
+    L.seg = o; o += SEG_STRIDE * (N + 3 * NMPC_SEG_UNR);  // + copies of the last segment: no remainder trips, prefetch overrun
+    L.circ = o; o += CIRC_STRIDE * (Nobs + 4);
     L.ell = o; o += ELL_STRIDE * Nd * N;
+    L.ebd = o; o += 4 * Nd;  // per dynamic obstacle: centre and squared radius of a disc around all its poses
     L.rho = o; o += 12;
     L.alpha = o; o += 12;
     L.hdr = o; o += H_COUNT;
-    L.vref = o; o += even_up(N);
-    L.job = o; o += (NMPC_HELP_R + 1) * (int)(JOB_BYTES / 8);  // line-search trials + one cost-evaluation record
+    L.vref = o; o += even_up(G * S);
     L.total = o;
     return L;
 }
@@ -140,7 +116,7 @@ struct KArgs {
     // eval kernel only
     const double* cvec;
     double *psi, *grad, *F1, *F2;
-    long long* dbg;  // NMPC_PROFILE builds only: 16 cycle counters per problem
+    long long* dbg;  // NMPC_PROFILE builds only: cycle counters per problem
 };
 #ifdef NMPC_PROFILE
 #define PROF_BEGIN() long long plast_ = clock64()
@@ -171,45 +147,20 @@ __device__ __forceinline__ void sts1(uint32_t a, double v) { asm volatile("st.sh
 __device__ __forceinline__ void sts2(uint32_t a, double2 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
 }
-// predicated forms (one instruction each, no branch): active lanes only
-__device__ __forceinline__ double2 lds2_if(uint32_t a, bool on) {
-    double2 v;
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
-                 "@p ld.shared.v2.f64 {%0, %1}, [%2];\n\t}"
-                 : "=d"(v.x), "=d"(v.y)
-                 : "r"(a), "r"((int)on));
-    return v;
-}
-__device__ __forceinline__ void sts2_if(uint32_t a, double2 v, bool on) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p st.shared.v2.f64 [%0], {%1, %2};\n\t}" ::"r"(a), "d"(v.x), "d"(v.y),
-                 "r"((int)on)
-                 : "memory");
+// one lane stores (predicated instruction, no divergent branch)
+__device__ __forceinline__ void sts1_if(uint32_t a, double v, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(a), "d"(v), "r"((int)on) : "memory");
 }
 __device__ __forceinline__ void stsi(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-
-// volatile / atomic access to the job words shared between warps of one CTA
-__device__ __forceinline__ int ldv_shared(uint32_t a) {
-    int v;
-    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ void stv_shared(uint32_t a, int v) { asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ int cas_shared(uint32_t a, int cmp, int val) {
-    int old;
-    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory");
-    return old;
-}
-__device__ __forceinline__ int add_shared(uint32_t a, int val) {
-    int old;
-    asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(val) : "memory");
-    return old;
-}
 
 // Rectangle::project of OpEn is comparison-based: a NaN stays a NaN (and ends the solve as NotFinite)
 __device__ __forceinline__ double clampd(double x, double lo, double hi) { return (x < lo) ? lo : ((x > hi) ? hi : x); }
 // min/max as compare-selects (same forms as the oracle): NaN -> the constant, zero results are +0
 // (written as setp/selp PTX: the C ternaries get canonicalised to max.f64/min.f64, which sm_100
 //  expands into a ~12-instruction DSETP.MAX/FSEL/SEL/NaN-fix-up sequence each)
+#ifndef NMPC_ICLAMP
+#define NMPC_ICLAMP 1  // round 2: -4 % cycles on the cross-track loop now that it is FP64-pipe bound
+#endif
 __device__ __forceinline__ double sel_clamp01(double t) {
 #if NMPC_ICLAMP
     // Same result as the two compare-selects for every non-NaN t, computed on the integer pipe from the
@@ -217,7 +168,7 @@ __device__ __forceinline__ double sel_clamp01(double t) {
     // lo' = lo only while 0 <= hi < hi(1.0).  Two FP64-pipe compares and four selects become four ALU ops.
     // (NaN: the selects give 0, this gives 0 or 1 by the sign bit; either way the distance stays NaN because
     //  a NaN projection parameter comes from a NaN point, which is already in ex/ey.)
-    double r;
+    double r0;
     asm("{\n\t.reg .b32 lo, hi, h2;\n\t.reg .pred p;\n\t"
         "mov.b64 {lo, hi}, %1;\n\t"
         "max.s32 h2, hi, 0;\n\t"
@@ -225,10 +176,10 @@ __device__ __forceinline__ double sel_clamp01(double t) {
         "setp.lt.u32 p, hi, 0x3FF00000;\n\t"
         "selp.b32 lo, lo, 0, p;\n\t"
         "mov.b64 %0, {lo, h2};\n\t}"
-        : "=d"(r)
+        : "=d"(r0)
         : "d"(t));
-    return r;
-#else
+    return r0;
+#endif
     double r;
     asm("{\n\t.reg .pred p;\n\t"
         "setp.gt.f64 p, %1, 0d0000000000000000;\n\tselp.f64 %0, %1, 0d0000000000000000, p;\n\t"
@@ -236,7 +187,6 @@ __device__ __forceinline__ double sel_clamp01(double t) {
         : "=d"(r)
         : "d"(t));
     return r;
-#endif
 }
 // if (d2 < best) { best = d2; bi = idx; }  — strict '<': the first minimal segment keeps the gradient
 __device__ __forceinline__ void take_if_less(double d2, int idx, double& best, int& bi) {
@@ -283,200 +233,90 @@ __device__ __forceinline__ void nm_sincos(double x, double& s, double& c) {
 }
 
 // ---------------------------------------------------------------------------------
-// warp-ordered reductions
-__device__ __forceinline__ double butterfly(double a) {
-    NMPC_STAGES
-    for (int off = 16; off; off >>= 1) a = a + __shfl_xor_sync(FULL, a, off);
+// group-ordered reductions: lane partials are serial sums over the lane's S steps (the callers
+// form them); these combine the G partials of a group.  Shuffle distances < G never leave an aligned group.
+template <int G>
+__device__ __forceinline__ double gsum(double a) {
+#pragma unroll
+    for (int off = G / 2; off; off >>= 1) a = a + __shfl_xor_sync(FULL, a, off);
     return a;
 }
-template <int P>
-__device__ __forceinline__ double hsum(const double (&e)[P]) {
-    double a = e[0];
+template <int G>
+__device__ __forceinline__ void gsum2(double& a, double& b) {
 #pragma unroll
-    for (int j = 1; j < P; j++) a = a + e[j];
-    return butterfly(a);
-}
-// two sums at once (interleaved shuffles)
-template <int P>
-__device__ __forceinline__ void hsum2(const double (&e)[P], const double (&f)[P], double& se, double& sf) {
-    double a = e[0], b = f[0];
-#pragma unroll
-    for (int j = 1; j < P; j++) {
-        a = a + e[j];
-        b = b + f[j];
-    }
-    NMPC_STAGES
-    for (int off = 16; off; off >>= 1) {
-        double ya = __shfl_xor_sync(FULL, a, off), yb = __shfl_xor_sync(FULL, b, off);
+    for (int off = G / 2; off; off >>= 1) {
+        const double ya = __shfl_xor_sync(FULL, a, off), yb = __shfl_xor_sync(FULL, b, off);
         a = a + ya;
         b = b + yb;
     }
-    se = a;
-    sf = b;
 }
-// four sums at once
-template <int P>
-__device__ __forceinline__ void hsum4(const double (&e0)[P], const double (&e1)[P], const double (&e2)[P],
-                                      const double (&e3)[P], double& s0, double& s1, double& s2, double& s3) {
-    double a = e0[0], b = e1[0], c = e2[0], d = e3[0];
+template <int G>
+__device__ __forceinline__ void gsum4(double& a, double& b, double& c, double& d) {
 #pragma unroll
-    for (int j = 1; j < P; j++) {
-        a = a + e0[j];
-        b = b + e1[j];
-        c = c + e2[j];
-        d = d + e3[j];
-    }
-    NMPC_STAGES
-    for (int off = 16; off; off >>= 1) {
-        double ya = __shfl_xor_sync(FULL, a, off), yb = __shfl_xor_sync(FULL, b, off);
-        double yc = __shfl_xor_sync(FULL, c, off), yd = __shfl_xor_sync(FULL, d, off);
+    for (int off = G / 2; off; off >>= 1) {
+        const double ya = __shfl_xor_sync(FULL, a, off), yb = __shfl_xor_sync(FULL, b, off);
+        const double yc = __shfl_xor_sync(FULL, c, off), yd = __shfl_xor_sync(FULL, d, off);
         a = a + ya;
         b = b + yb;
         c = c + yc;
         d = d + yd;
     }
-    s0 = a;
-    s1 = b;
-    s2 = c;
-    s3 = d;
 }
-template <int P>
-__device__ __forceinline__ void prefix_scan(const double (&x)[P], double (&incl)[P], double (&excl)[P], int lane) {
-    double carry = 0.0;
+// Kogge-Stone inclusive scan of the lane totals over the group; returns the EXCLUSIVE prefix of this lane
+// (the scanned total of lane gl-1; 0.0 for the first lane)
+template <int G>
+__device__ __forceinline__ double gscan_up_excl(double T, int gl) {
 #pragma unroll
-    for (int j = 0; j < P; j++) {
-        double l = x[j];
-        NMPC_STAGES
-        for (int off = 1; off < 32; off <<= 1) {
-            double y = __shfl_up_sync(FULL, l, off);
-            add_if(l, y, lane >= off);
-        }
-        double lm1 = __shfl_up_sync(FULL, l, 1);
-        double g = (j == 0) ? l : carry + l;
-        excl[j] = (lane == 0) ? carry : ((j == 0) ? lm1 : carry + lm1);
-        incl[j] = g;
-        if (j + 1 < P) carry = __shfl_sync(FULL, g, 31);
+    for (int off = 1; off < G; off <<= 1) {
+        const double y = __shfl_up_sync(FULL, T, off, G);
+        add_if(T, y, gl >= off);
     }
+    const double E = __shfl_up_sync(FULL, T, 1, G);
+    return gl == 0 ? 0.0 : E;
 }
-template <int P>
-__device__ __forceinline__ void prefix_scan2(const double (&xa)[P], const double (&xb)[P], double (&ia)[P],
-                                             double (&ea)[P], double (&ib)[P], double (&eb)[P], int lane) {
-    double ca = 0.0, cb = 0.0;
+template <int G>
+__device__ __forceinline__ void gscan_up_excl2(double Ta, double Tb, int gl, double& Ea, double& Eb) {
 #pragma unroll
-    for (int j = 0; j < P; j++) {
-        double la = xa[j], lb = xb[j];
-        NMPC_STAGES
-        for (int off = 1; off < 32; off <<= 1) {
-            double ya = __shfl_up_sync(FULL, la, off);
-            double yb = __shfl_up_sync(FULL, lb, off);
-            add_if(la, ya, lane >= off);
-            add_if(lb, yb, lane >= off);
-        }
-        double ma = __shfl_up_sync(FULL, la, 1), mb = __shfl_up_sync(FULL, lb, 1);
-        double ga = (j == 0) ? la : ca + la, gb = (j == 0) ? lb : cb + lb;
-        ea[j] = (lane == 0) ? ca : ((j == 0) ? ma : ca + ma);
-        eb[j] = (lane == 0) ? cb : ((j == 0) ? mb : cb + mb);
-        ia[j] = ga;
-        ib[j] = gb;
-        if (j + 1 < P) {
-            ca = __shfl_sync(FULL, ga, 31);
-            cb = __shfl_sync(FULL, gb, 31);
-        }
+    for (int off = 1; off < G; off <<= 1) {
+        const double ya = __shfl_up_sync(FULL, Ta, off, G), yb = __shfl_up_sync(FULL, Tb, off, G);
+        add_if(Ta, ya, gl >= off);
+        add_if(Tb, yb, gl >= off);
     }
+    Ea = __shfl_up_sync(FULL, Ta, 1, G);
+    Eb = __shfl_up_sync(FULL, Tb, 1, G);
+    Ea = gl == 0 ? 0.0 : Ea;
+    Eb = gl == 0 ? 0.0 : Eb;
 }
-template <int P>
-__device__ __forceinline__ void suffix_scan(const double (&x)[P], double (&suf)[P], int lane) {
-    double carry = 0.0;
+// suffix direction: exclusive suffix = scanned total of lane gl+1 (0.0 for the last lane)
+template <int G>
+__device__ __forceinline__ double gscan_down_excl(double T, int gl) {
 #pragma unroll
-    for (int j = P - 1; j >= 0; j--) {
-        double l = x[j];
-        NMPC_STAGES
-        for (int off = 1; off < 32; off <<= 1) {
-            double y = __shfl_down_sync(FULL, l, off);
-            add_if(l, y, lane + off < 32);
-        }
-        double g = (j == P - 1) ? l : carry + l;
-        suf[j] = g;
-        if (j > 0) carry = __shfl_sync(FULL, g, 0);
+    for (int off = 1; off < G; off <<= 1) {
+        const double y = __shfl_down_sync(FULL, T, off, G);
+        add_if(T, y, gl + off < G);
     }
+    const double E = __shfl_down_sync(FULL, T, 1, G);
+    return gl == G - 1 ? 0.0 : E;
 }
-template <int P>
-__device__ __forceinline__ void suffix_scan2(const double (&xa)[P], const double (&xb)[P], double (&sa)[P],
-                                             double (&sb)[P], int lane) {
-    double ca = 0.0, cb = 0.0;
+// two suffix scans with an independent group sum riding along in the same instruction stream
+template <int G>
+__device__ __forceinline__ void gscan_down_excl2_sum(double Ta, double Tb, int gl, double& Ea, double& Eb, double& acc) {
+    int st = G / 2;
 #pragma unroll
-    for (int j = P - 1; j >= 0; j--) {
-        double la = xa[j], lb = xb[j];
-        NMPC_STAGES
-        for (int off = 1; off < 32; off <<= 1) {
-            double ya = __shfl_down_sync(FULL, la, off);
-            double yb = __shfl_down_sync(FULL, lb, off);
-            add_if(la, ya, lane + off < 32);
-            add_if(lb, yb, lane + off < 32);
-        }
-        double ga = (j == P - 1) ? la : ca + la, gb = (j == P - 1) ? lb : cb + lb;
-        sa[j] = ga;
-        sb[j] = gb;
-        if (j > 0) {
-            ca = __shfl_sync(FULL, ga, 0);
-            cb = __shfl_sync(FULL, gb, 0);
-        }
+    for (int off = 1; off < G; off <<= 1, st >>= 1) {
+        const double ya = __shfl_down_sync(FULL, Ta, off, G), yb = __shfl_down_sync(FULL, Tb, off, G);
+        const double yc = __shfl_xor_sync(FULL, acc, st);
+        add_if(Ta, ya, gl + off < G);
+        add_if(Tb, yb, gl + off < G);
+        acc = acc + yc;
     }
-}
-// suffix_scan2 with an independent xor-butterfly sum riding along in the same instruction stream: the stages of
-// the two reductions interleave, so the cost sum of a gradient evaluation costs no extra latency.
-// Each of the three results is bit-identical to suffix_scan2 / hsum.
-template <int P>
-__device__ __forceinline__ void suffix_scan2_hsum(const double (&xa)[P], const double (&xb)[P], double (&sa)[P],
-                                                  double (&sb)[P], const double (&e)[P], double& esum, int lane) {
-    double acc = e[0];
-#pragma unroll
-    for (int j = 1; j < P; j++) acc = acc + e[j];
-    double ca = 0.0, cb = 0.0;
-#pragma unroll
-    for (int j = P - 1; j >= 0; j--) {
-        double la = xa[j], lb = xb[j];
-        NMPC_STAGES
-        for (int st = 0; st < 5; st++) {
-            const int off = 1 << st;
-            double ya = __shfl_down_sync(FULL, la, off);
-            double yb = __shfl_down_sync(FULL, lb, off);
-            double yc = 0.0;
-            if (j == P - 1) yc = __shfl_xor_sync(FULL, acc, 16 >> st);
-            add_if(la, ya, lane + off < 32);
-            add_if(lb, yb, lane + off < 32);
-            if (j == P - 1) acc = acc + yc;
-        }
-        double ga = (j == P - 1) ? la : ca + la, gb = (j == P - 1) ? lb : cb + lb;
-        sa[j] = ga;
-        sb[j] = gb;
-        if (j > 0) {
-            ca = __shfl_sync(FULL, ga, 0);
-            cb = __shfl_sync(FULL, gb, 0);
-        }
-    }
-    esum = acc;
-}
-template <int P>
-__device__ __forceinline__ double wdot(const double2 (&a)[P], const double2 (&b)[P]) {
-    double e[P];
-#pragma unroll
-    for (int j = 0; j < P; j++) e[j] = fma(a[j].y, b[j].y, a[j].x * b[j].x);
-    return hsum<P>(e);
-}
-template <int P>
-__device__ __forceinline__ double wdiff2(const double2 (&a)[P], const double2 (&b)[P]) {
-    double e[P];
-#pragma unroll
-    for (int j = 0; j < P; j++) {
-        double d0 = a[j].x - b[j].x, d1 = a[j].y - b[j].y;
-        e[j] = fma(d1, d1, d0 * d0);
-    }
-    return hsum<P>(e);
+    Ea = __shfl_down_sync(FULL, Ta, 1, G);
+    Eb = __shfl_down_sync(FULL, Tb, 1, G);
+    Ea = gl == G - 1 ? 0.0 : Ea;
+    Eb = gl == G - 1 ? 0.0 : Eb;
 }
 
 // ---------------------------------------------------------------------------------
-enum { MODE_COST = 0, MODE_GRAD = 1, MODE_F2 = 2 };
 struct Pen {
     double c, hc, inv_c;
 };
@@ -489,65 +329,59 @@ __device__ __forceinline__ Pen make_pen(double c) {
 }
 
 // One warp's view of its problem: arena addresses + lane mapping.
-// NF > 0: the horizon is a compile-time constant (NF == cfg.N_hor, checked by the host): the cross-track
-// loop is fully unrolled with a tree arg-min, so a lone warp (the tail of a small batch) gets ILP.
-template <int P, int NF = 0>
+template <int G, int S>
 struct Warp {
+    static constexpr int NG = 32 / G;  // evaluation groups
     const nmpc_config& cfg;
-    uint32_t sb;         // shared byte address of the arena
-    uint32_t la[P];      // sb + 16*t : this lane's element inside vector 0
-    uint32_t vstride;    // bytes per vector (2N doubles)
-    uint32_t a_seg, a_circ, a_ell, a_rho, a_alpha, a_hdr, a_vref, a_job;
-    uint32_t sb0, arena_bytes;  // arena of warp 0 / bytes per arena (retarget)
-    int lane, n_circ;    // n_circ: circles with r != 0 (zero-padded slots are skipped: they add exact zeros)
-    bool act[P];
-    int tix[P];
+    uint32_t sb;       // shared byte address of the arena
+    uint32_t la;       // sb + 16*gl : this lane's element of slot row 0 inside vector 0
+    uint32_t vstride;  // bytes per vector
+    uint32_t a_seg, a_circ, a_ell, a_ebd, a_rho, a_alpha, a_hdr, a_vref;
+    int lane, grp, gl, N, n_circ;  // n_circ: circles with r != 0 (zero-padded slots are skipped: they add exact zeros)
+    bool act[S];
+    int tix[S];
 #ifdef NMPC_PROFILE
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cycles per eval section (tools/prof_cycles.py)
 #endif
 
     __device__ __forceinline__ Warp(const nmpc_config& c, const Lay& L, int warp, int lane_) : cfg(c), lane(lane_) {
-        sb0 = (uint32_t)__cvta_generic_to_shared(smem);
-        arena_bytes = (uint32_t)L.total * 8u;
-        sb = sb0 + (uint32_t)warp * arena_bytes;
-        vstride = (uint32_t)L.n2 * 8u;
-        a_seg = sb + L.seg * 8u; a_circ = sb + L.circ * 8u; a_ell = sb + L.ell * 8u; a_rho = sb + L.rho * 8u;
-        a_alpha = sb + L.alpha * 8u; a_hdr = sb + L.hdr * 8u; a_vref = sb + L.vref * 8u; a_job = sb + L.job * 8u;
+        grp = lane / G;
+        gl = lane % G;
+        N = cfg.N_hor;
+        sb = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)warp * (uint32_t)L.total * 8u;
+        la = sb + 16u * gl;
+        vstride = (uint32_t)L.vlen * 8u;
+        a_seg = sb + L.seg * 8u; a_circ = sb + L.circ * 8u; a_ell = sb + L.ell * 8u; a_ebd = sb + L.ebd * 8u; a_rho = sb + L.rho * 8u;
+        a_alpha = sb + L.alpha * 8u; a_hdr = sb + L.hdr * 8u; a_vref = sb + L.vref * 8u;
         n_circ = 0;
 #pragma unroll
-        for (int j = 0; j < P; j++) {
-            tix[j] = lane + 32 * j;
-            act[j] = tix[j] < (NF ? NF : cfg.N_hor);
-            la[j] = sb + 16u * tix[j];
+        for (int s = 0; s < S; s++) {
+            tix[s] = S * gl + s;
+            act[s] = tix[s] < N;
         }
     }
-    // point this view at the arena of warp `o` of the CTA (a helper warp evaluates another warp's problem there)
-    __device__ __forceinline__ void retarget(int o) {
-        const uint32_t nsb = sb0 + (uint32_t)o * arena_bytes, d = nsb - sb;
-        sb = nsb;
-        a_seg += d; a_circ += d; a_ell += d; a_rho += d; a_alpha += d; a_hdr += d; a_vref += d; a_job += d;
-#pragma unroll
-        for (int j = 0; j < P; j++) la[j] += d;
-        n_circ = ldsi(a_hdr + 8u * H_NCIRC);
-    }
     __device__ __forceinline__ double hdr(int i) const { return lds1(a_hdr + 8u * i); }
-    __device__ __forceinline__ void ld(int k, double2 (&r)[P]) const {
+    // vector k of the arena: every lane reads its S (v, w) pairs; all groups see the same vector
+    __device__ __forceinline__ void ld(int k, double2 (&r)[S]) const {
 #pragma unroll
-        for (int j = 0; j < P; j++) r[j] = lds2_if(la[j] + k * vstride, act[j]);
+        for (int s = 0; s < S; s++) r[s] = lds2(la + k * vstride + 16u * G * s);
     }
-    __device__ __forceinline__ void st(int k, const double2 (&r)[P]) const {
+    // stores come from ONE group (by default group 0; `from` = the group whose registers hold the vector)
+    __device__ __forceinline__ void st(int k, const double2 (&r)[S], int from = 0) const {
+        if (grp == from) {
 #pragma unroll
-        for (int j = 0; j < P; j++) sts2_if(la[j] + k * vstride, r[j], act[j]);
+            for (int s = 0; s < S; s++) sts2(la + k * vstride + 16u * G * s, r[s]);
+        }
     }
 
     // unpack the parameter row (layout: include/nmpc_b200.h) into the arena
     __device__ void stage(const double* __restrict__ p) {
-        const int N = NF ? NF : cfg.N_hor, Nobs = cfg.Nobs, Nd = cfg.Ndynobs;
+        const int Nobs = cfg.Nobs, Nd = cfg.Ndynobs;
         __syncwarp();
         if (lane < 8) sts1(a_hdr + 8u * lane, p[lane]);
         if (lane >= 8 && lane < 18) sts1(a_hdr + 8u * lane, p[lane + 2]);
         if (lane == 18) sts1(a_hdr + 8u * H_INVTS, 1.0 / cfg.ts);
-        for (int t = lane; t < N; t += 32) sts1(a_vref + 8u * t, p[NMPC_NZ + t]);
+        for (int t = lane; t < G * S; t += 32) sts1(a_vref + 8u * t, t < N ? p[NMPC_NZ + t] : 0.0);
         const double* pc = p + NMPC_NZ + N;
         int nreal = 0;
         for (int k0 = 0; k0 < Nobs; k0 += 32) {  // order-preserving compaction of the non-padded circles
@@ -569,6 +403,12 @@ struct Warp {
             }
             nreal += __popc(m);
         }
+        if (lane < 4) {  // the circle loop reads four at a time: dummies that can never be entered (r^2 = -1)
+            const uint32_t a = a_circ + 32u * (nreal + lane);
+            sts2(a, make_double2(0.0, 0.0));
+            sts1(a + 16u, -1.0);
+            stsi(a + 24u, 0);
+        }
         n_circ = nreal;
         if (lane == 0) stsi(a_hdr + 8u * H_NCIRC, nreal);
         const double* pe = pc + 3 * Nobs;
@@ -582,10 +422,35 @@ struct Warp {
             sts2(a + 16u, make_double2(ca, sa));
             sts2(a + 32u, make_double2(1.0 / (e[2] * e[2]), 1.0 / (e[3] * e[3])));
         }
+        // A disc that contains every pose of dynamic obstacle k over the horizon (plus a relative margin far above
+        // rounding): a predicted point outside it is outside the ellipse at every step, so eval() can skip the
+        // obstacle without changing a bit (it would add exact zeros).  NaN / inf parameters give a NaN radius: the
+        // test `inside the disc` is then false for every point, and so is the ellipse test itself.
+        for (int k = lane; k < Nd; k += 32) {
+            const double* e = pe + 5 * (size_t)k * N;
+            double xlo = e[0], xhi = e[0], ylo = e[1], yhi = e[1];
+            for (int t = 1; t < N; t++) {
+                xlo = fmin(xlo, e[5 * t]); xhi = fmax(xhi, e[5 * t]);
+                ylo = fmin(ylo, e[5 * t + 1]); yhi = fmax(yhi, e[5 * t + 1]);
+            }
+            const double bx = 0.5 * (xlo + xhi), by = 0.5 * (ylo + yhi);
+            double R = 0.0;
+            bool bad = false;
+            for (int t = 0; t < N; t++) {
+                const double ddx = e[5 * t] - bx, ddy = e[5 * t + 1] - by;
+                const double r = sqrt(ddx * ddx + ddy * ddy) + fmax(fabs(e[5 * t + 2]), fabs(e[5 * t + 3]));
+                bad = bad || !(r == r) || !(e[5 * t + 4] == e[5 * t + 4]);
+                R = fmax(R, r);
+            }
+            R = R * (1.0 + 1e-6) + 1e-9;
+            const uint32_t a = a_ebd + 32u * k;
+            sts2(a, make_double2(bx, by));
+            sts1(a + 16u, bad ? CUDART_NAN : R * R);
+        }
         const double* pr = pe + 5 * ne;
-        for (int ii = lane; ii < N + SEG_PAD; ii += 32) {
+        for (int ii = lane; ii < N + 3 * NMPC_SEG_UNR; ii += 32) {
             if (ii >= 1) {
-                // slots N .. N+SEG_PAD-1 repeat segment N-1: equal distances never win the strict '<' arg-min
+                // slots N .. repeat segment N-1: equal distances never win the strict '<' arg-min
                 const int i = (ii < N) ? ii : N - 1;
                 double ax = pr[3 * (i - 1)], ay = pr[3 * (i - 1) + 1];
                 double dx = pr[3 * i] - ax, dy = pr[3 * i + 1] - ay;
@@ -598,378 +463,359 @@ struct Warp {
         __syncwarp();
     }
 
-    // previous step's control for lane-distributed (v, w): lane-1, pass carry, or (v_init, w_init)
-    __device__ __forceinline__ void prev_controls(const double2 (&uv)[P], int j, double& vp, double& wp) const {
-        vp = __shfl_up_sync(FULL, uv[j].x, 1);
-        wp = __shfl_up_sync(FULL, uv[j].y, 1);
-        if (j > 0) {
-            double v31 = __shfl_sync(FULL, uv[j > 0 ? j - 1 : 0].x, 31), w31 = __shfl_sync(FULL, uv[j > 0 ? j - 1 : 0].y, 31);
-            if (lane == 0) {
-                vp = v31;
-                wp = w31;
-            }
-        } else if (lane == 0) {
-            vp = hdr(H_VINIT);
-            wp = hdr(H_WINIT);
+    // control of the step before this lane's step s: in-lane, the previous lane's last step, or (v_init, w_init)
+    __device__ __forceinline__ void prev_controls(const double2 (&uv)[S], double& vp0, double& wp0) const {
+        vp0 = __shfl_up_sync(FULL, uv[S - 1].x, 1, G);
+        wp0 = __shfl_up_sync(FULL, uv[S - 1].y, 1, G);
+        if (gl == 0) {
+            vp0 = hdr(H_VINIT);
+            wp0 = hdr(H_WINIT);
         }
     }
 
-    // psi / grad psi / F2 for the staged problem (mode is warp-uniform)
-    __device__ double eval(const int mode, const double2 (&uv)[P], const Pen pn, const double2 (&yl)[P],
-                           double2 (&gout)[P], double& pen_out, double* __restrict__ F2g) {
-        const bool GRAD = (mode == MODE_GRAD);
-        const int N = NF ? NF : cfg.N_hor;
+    // psi, grad psi and |F2|^2 of the staged problem at this GROUP's point uv (every group evaluates its own
+    // point with its own penalty parameter; the multipliers come from the arena vector V_YL)
+    __device__ double eval(const double2 (&uv)[S], const Pen pn, double2 (&gout)[S], double& pen_out,
+                           double* __restrict__ F2g) {
         const double ts = cfg.ts;
         PROF_BEGIN();
-        double tw[P], inclT[P], exclT[P];
+        // ---- rollout (src/mpc/mpc_generator.py:88-90): heading by a scan of ts*w, position by a joint scan
+        double cth[S];
 #pragma unroll
-        for (int j = 0; j < P; j++) tw[j] = act[j] ? ts * uv[j].y : 0.0;
-        prefix_scan<P>(tw, inclT, exclT, lane);
-        double sn[P], cs[P], thpre[P], TH[P], a[P], b[P];
-        const double th0 = hdr(H_TH0);
-#pragma unroll
-        for (int j = 0; j < P; j++) {
-            thpre[j] = th0 + exclT[j];
-            TH[j] = th0 + inclT[j];
-            nm_sincos(thpre[j], sn[j], cs[j]);
-            a[j] = act[j] ? ts * (uv[j].x * cs[j]) : 0.0;
-            b[j] = act[j] ? ts * (uv[j].x * sn[j]) : 0.0;
+        for (int s = 0; s < S; s++) {
+            const double v = act[s] ? ts * uv[s].y : 0.0;
+            cth[s] = (s == 0) ? v : cth[s - 1] + v;
         }
-        PROF_MARK(0);
-        double X[P], Y[P], xpre[P], ypre[P];
-        {
-            double ia[P], ea[P], ib[P], eb[P];
-            prefix_scan2<P>(a, b, ia, ea, ib, eb, lane);
-            const double x0 = hdr(H_X0), y0 = hdr(H_Y0);
+        const double Eth = gscan_up_excl<G>(cth[S - 1], gl);
+        const double th0 = hdr(H_TH0);
+        const double thp0 = th0 + Eth;  // heading before this lane's first step
+        double TH[S], sn[S], cs[S];
 #pragma unroll
-            for (int j = 0; j < P; j++) {
-                xpre[j] = x0 + ea[j];
-                ypre[j] = y0 + eb[j];
-                X[j] = x0 + ia[j];
-                Y[j] = y0 + ib[j];
+        for (int s = 0; s < S; s++) TH[s] = th0 + (Eth + cth[s]);
+#pragma unroll
+        for (int s = 0; s < S; s++) nm_sincos(s == 0 ? thp0 : TH[s > 0 ? s - 1 : 0], sn[s], cs[s]);
+        PROF_MARK(0);
+        double X[S], Y[S], xp0, yp0;
+        {
+            double ca[S], cb[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const double va = act[s] ? ts * (uv[s].x * cs[s]) : 0.0;
+                const double vb = act[s] ? ts * (uv[s].x * sn[s]) : 0.0;
+                ca[s] = (s == 0) ? va : ca[s - 1] + va;
+                cb[s] = (s == 0) ? vb : cb[s - 1] + vb;
+            }
+            double Ea, Eb;
+            gscan_up_excl2<G>(ca[S - 1], cb[S - 1], gl, Ea, Eb);
+            const double x0 = hdr(H_X0), y0 = hdr(H_Y0);
+            xp0 = x0 + Ea;
+            yp0 = y0 + Eb;
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                X[s] = x0 + (Ea + ca[s]);
+                Y[s] = y0 + (Eb + cb[s]);
             }
         }
-        double gX[P], gY[P], mind2[P];
-#pragma unroll
-        for (int j = 0; j < P; j++) gX[j] = gY[j] = mind2[j] = 0.0;
-        const double qcte = hdr(H_QCTE);
         PROF_MARK(1);
 
-        if (mode != MODE_F2) {
-            // cross-track error: each lane scans the N-1 segments for its own predicted point
-            double best[P];
-            int bi[P];
+        // ---- cross-track error (:122-144): every lane scans the N-1 segments for its S predicted points
+        double gX[S], gY[S], mind2[S];
+        const double qcte = hdr(H_QCTE);
+        {
+            double best[S];
+            int bi[S];
 #pragma unroll
-            for (int j = 0; j < P; j++) {
-                best[j] = CUDART_INF;
-                bi[j] = 1;
+            for (int s = 0; s < S; s++) {
+                best[s] = CUDART_INF;
+                bi[s] = 1;
             }
-            if constexpr (NF > 0 && P == 1) {
-                // all NF-1 segments are independent; arg-min by a tree whose left operand holds the lower
-                // indices and wins ties (= the first minimal segment, as the serial strict-'<' scan)
-                double dv[NF - 1];
-                int iv[NF - 1];
+            constexpr int U = NMPC_SEG_UNR;
+            struct Seg {
+                double2 s1[U], d[U];
+                double inv[U];
+            };
+            auto ldseg = [&](uint32_t a, Seg& g) {
 #pragma unroll
-                for (int i = 1; i < NF; i++) {
-                    const uint32_t as = a_seg + 48u * i;
-                    const double2 s1 = lds2(as), d = lds2(as + 16u);
-                    const double inv = lds1(as + 32u);
-                    double px = X[0] - s1.x, py = Y[0] - s1.y;
-                    double that = fma(px, d.x, py * d.y) * inv;
-                    double tst = sel_clamp01(that);
-                    double ex = fma(tst, d.x, -px), ey = fma(tst, d.y, -py);
-                    dv[i - 1] = fma(ex, ex, ey * ey);
-                    iv[i - 1] = i;
+                for (int q = 0; q < U; q++) {
+                    g.s1[q] = lds2(a + 48u * q);
+                    g.d[q] = lds2(a + 48u * q + 16u);
+                    g.inv[q] = lds1(a + 48u * q + 32u);
                 }
+            };
+            auto body = [&](int i, const Seg& g) {
+                double d2[U][S];
 #pragma unroll
-                for (int st = 1; st < NF - 1; st *= 2)
+                for (int q = 0; q < U; q++)
 #pragma unroll
-                    for (int k = 0; k + st < NF - 1; k += 2 * st) take_if_less(dv[k + st], iv[k + st], dv[k], iv[k]);
-                take_if_less(dv[0], iv[0], best[0], bi[0]);
-            } else {
-            constexpr int UNR = (P == 1) ? 4 : 2;
-            uint32_t as = a_seg + 48u;
-            int i = 1;
-            // UNR segments per trip, written stage by stage: the SM issues in order, so independent
-            // chains only overlap if they are interleaved in the instruction stream
-            NMPC_NOUNROLL
-            for (; i < N; i += UNR, as += 48u * UNR) {
-                double2 s1[UNR], d[UNR];
-                double inv[UNR];
-#pragma unroll
-                for (int q = 0; q < UNR; q++) {
-                    s1[q] = lds2(as + 48u * q);
-                    d[q] = lds2(as + 48u * q + 16u);
-                    inv[q] = lds1(as + 48u * q + 32u);
-                }
-#pragma unroll
-                for (int j = 0; j < P; j++) {
-                    int iq[UNR];
-                    double d2[UNR];
-#pragma unroll
-                    for (int q = 0; q < UNR; q++) {
-                        double px = X[j] - s1[q].x, py = Y[j] - s1[q].y;
-                        double that = fma(px, d[q].x, py * d[q].y) * inv[q];
-                        double tst = sel_clamp01(that);
-                        double ex = fma(tst, d[q].x, -px), ey = fma(tst, d[q].y, -py);
-                        d2[q] = fma(ex, ex, ey * ey);
+                    for (int s = 0; s < S; s++) {
+                        const double px = X[s] - g.s1[q].x, py = Y[s] - g.s1[q].y;
+                        const double that = fma(px, g.d[q].x, py * g.d[q].y) * g.inv[q];
+                        const double tst = sel_clamp01(that);
+                        const double ex = fma(tst, g.d[q].x, -px), ey = fma(tst, g.d[q].y, -py);
+                        d2[q][s] = fma(ex, ex, ey * ey);
                     }
 #pragma unroll
-                    for (int q = 0; q < UNR; q++) iq[q] = i + q;
-                    // arg-min of the trip as a tree (the left operand holds the lower indices and wins ties, like the
-                    // serial strict-'<' scan), then ONE merge into the running minimum: the chain between trips is short
+                for (int q = 0; q < U; q++)
 #pragma unroll
-                    for (int st = 1; st < UNR; st *= 2)
-#pragma unroll
-                        for (int q = 0; q + st < UNR; q += 2 * st) take_if_less(d2[q + st], iq[q + st], d2[q], iq[q]);
-                    take_if_less(d2[0], iq[0], best[j], bi[j]);
-                }
+                    for (int s = 0; s < S; s++) take_if_less(d2[q][s], i + q, best[s], bi[s]);
+            };
+            // two half-trips per trip, each working on segments fetched one half-trip earlier (no moves, the loads
+            // of the next half-trip are in flight behind the arithmetic of this one)
+            Seg ga, gb;
+            uint32_t as = a_seg + 48u;
+            ldseg(as, ga);
+#pragma unroll 1
+            for (int i = 1; i < N; i += 2 * U, as += 96u * U) {
+                ldseg(as + 48u * U, gb);
+                body(i, ga);
+                ldseg(as + 96u * U, ga);
+                body(i + U, gb);
             }
-            }
 #pragma unroll
-            for (int j = 0; j < P; j++) {
-                mind2[j] = best[j];
-                if (GRAD) {  // redo the arg-min segment (same operations, same bits) for the gradient
-                    const uint32_t ab = a_seg + 48u * bi[j];
-                    const double2 s1 = lds2(ab), d = lds2(ab + 16u);
-                    const double inv = lds1(ab + 32u);
-                    double px = X[j] - s1.x, py = Y[j] - s1.y;
-                    double that = fma(px, d.x, py * d.y) * inv;
-                    double tst = sel_clamp01(that);
-                    double ex = fma(tst, d.x, -px), ey = fma(tst, d.y, -py);
-                    double ed = (that >= 0.0 && that <= 1.0) ? fma(ex, d.x, ey * d.y) * inv : 0.0;
-                    double k2 = 2.0 * qcte;
-                    gX[j] = k2 * fma(ed, d.x, -ex);
-                    gY[j] = k2 * fma(ed, d.y, -ey);
-                }
+            for (int s = 0; s < S; s++) {  // redo the arg-min segment (same operations, same bits) for the gradient
+                mind2[s] = best[s];
+                const uint32_t ab = a_seg + 48u * bi[s];
+                const double2 s1 = lds2(ab), d = lds2(ab + 16u);
+                const double inv = lds1(ab + 32u);
+                const double px = X[s] - s1.x, py = Y[s] - s1.y;
+                const double that = fma(px, d.x, py * d.y) * inv;
+                const double tst = sel_clamp01(that);
+                const double ex = fma(tst, d.x, -px), ey = fma(tst, d.y, -py);
+                const double ed = (that >= 0.0 && that <= 1.0) ? fma(ex, d.x, ey * d.y) * inv : 0.0;
+                const double k2 = 2.0 * qcte;
+                gX[s] = k2 * fma(ed, d.x, -ex);
+                gY[s] = k2 * fma(ed, d.y, -ey);
             }
         }
-
         PROF_MARK(2);
-        // obstacle penalty F2: circles (non-padded ones), then this lane's time slice of each ellipse.
-        // Obstacles are tested in chunks: all inside-tests and votes of a chunk are issued back to back and
-        // ONE branch decides whether any of them needs the (rare) ordered time-sum + gradient path.
+
+        // ---- obstacle penalty F2 (:106-119): F2_k = sum over the horizon of max(0, inside_k(t)).
+        // All inside-tests of a chunk are issued back to back and ONE warp-wide vote decides whether any group
+        // needs the group sums and gradient terms (skipping adds exact zeros only).
         double pen = 0.0;
-        auto ordered_sum = [&](const double(&h)[P], const unsigned(&m)[P]) {
-            double g = 0.0;  // sum over active steps in ascending t (skipped terms are exact zeros)
-#pragma unroll
-            for (int j = 0; j < P; j++) {
-                unsigned mm = m[j];
-                while (mm) {
-                    int src = __ffs(mm) - 1;
-                    g = g + __shfl_sync(FULL, h[j], src);
-                    mm &= mm - 1;
-                }
-            }
-            return g;
-        };
         {
-            constexpr int CH = (P == 1) ? 4 : 2;
-            uint32_t ac = a_circ;
-            for (int k0 = 0; k0 < n_circ; k0 += CH, ac += 32u * CH) {
-                double h[CH][P], dx[CH][P], dy[CH][P];
-                unsigned m[CH][P];
-                unsigned any = 0;
+            // pass 1: the inside-tests of all circles back to back (no votes, no branches: the chains overlap); every
+            // lane notes the circles one of its points is inside of, one warp-wide OR gives the circles that need
+            // pass 2 (group sum, penalty, gradient) — rarely any.  32 circles per round.
+#pragma unroll 1
+            for (int kb = 0; kb < n_circ; kb += 32) {
+                const int kn = min(32, n_circ - kb);
+                unsigned mine = 0;
+                uint32_t ac = a_circ + 32u * kb;
+#pragma unroll 1
+                for (int k = 0; k < kn; k += 4, ac += 128u) {
 #pragma unroll
-                for (int q = 0; q < CH; q++) {
-                    const bool valid = (k0 + q) < n_circ;  // warp-uniform; slots past n_circ hold stale data
-                    const double2 cxy = lds2(ac + 32u * q);
-                    const double r2 = lds1(ac + 32u * q + 16u);
+                    for (int q = 0; q < 4; q++) {
+                        const double2 cxy = lds2(ac + 32u * q);
+                        const double r2 = lds1(ac + 32u * q + 16u);  // the slot behind the last circle holds r^2 = -1
+                        bool in = false;
 #pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        dx[q][j] = X[j] - cxy.x;
-                        dy[q][j] = Y[j] - cxy.y;
-                        const double hh = fma(-dy[q][j], dy[q][j], fma(-dx[q][j], dx[q][j], r2));
-                        h[q][j] = valid ? hh : -1.0;
+                        for (int s = 0; s < S; s++) {
+                            const double dx = X[s] - cxy.x, dy = Y[s] - cxy.y;
+                            in = in || (act[s] && fma(-dy, dy, fma(-dx, dx, r2)) > 0.0);
+                        }
+                        mine |= in ? (1u << (k + q)) : 0u;
                     }
                 }
+                unsigned todo = __reduce_or_sync(FULL, mine);
+                while (todo) {
+                    const int k = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const uint32_t a1 = a_circ + 32u * (kb + k);
+                    const double2 cxy = lds2(a1);
+                    const double r2 = lds1(a1 + 16u);
+                    double hp[S], dx[S], dy[S];
 #pragma unroll
-                for (int q = 0; q < CH; q++)
-#pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        m[q][j] = __ballot_sync(FULL, act[j] && h[q][j] > 0.0);
-                        any |= m[q][j];
+                    for (int s = 0; s < S; s++) {
+                        dx[s] = X[s] - cxy.x;
+                        dy[s] = Y[s] - cxy.y;
+                        const double hh = fma(-dy[s], dy[s], fma(-dx[s], dx[s], r2));
+                        hp[s] = (act[s] && hh > 0.0) ? hh : 0.0;
                     }
-                if (any) {
+                    double g = hp[0];
 #pragma unroll
-                    for (int q = 0; q < CH; q++) {
-                        unsigned anyq = 0;
+                    for (int s = 1; s < S; s++) g = g + hp[s];
+                    g = gsum<G>(g);
+                    if (F2g && lane == 0 && g > 0.0) F2g[ldsi(a1 + 24u)] = g;
+                    pen = fma(g, g, pen);
+                    const double cg = pn.c * g;
 #pragma unroll
-                        for (int j = 0; j < P; j++) anyq |= m[q][j];
-                        if (anyq) {
-                            const double g = ordered_sum(h[q], m[q]);
-                            if (F2g && lane == 0) F2g[ldsi(ac + 32u * q + 24u)] = g;
-                            pen = fma(g, g, pen);
-                            if (GRAD && g > 0.0) {
-                                const double cg = pn.c * g;
-#pragma unroll
-                                for (int j = 0; j < P; j++)
-                                    if (act[j] && h[q][j] > 0.0) {
-                                        gX[j] = fma(cg, -2.0 * dx[q][j], gX[j]);
-                                        gY[j] = fma(cg, -2.0 * dy[q][j], gY[j]);
-                                    }
-                            }
+                    for (int s = 0; s < S; s++)
+                        if (hp[s] > 0.0) {
+                            gX[s] = fma(cg, -2.0 * dx[s], gX[s]);
+                            gY[s] = fma(cg, -2.0 * dy[s], gY[s]);
                         }
-                    }
                 }
             }
-            constexpr int CE = (P == 1) ? 3 : 1;
             const int Nd = cfg.Ndynobs;
-            for (int k0 = 0; k0 < Nd; k0 += CE) {
-                double h[CE][P], ta[CE][P], tb[CE][P], eca[CE][P], esa[CE][P];
-                unsigned m[CE][P];
-                unsigned any = 0;
+#pragma unroll 1
+            for (int k = 0; k < Nd; k++) {
+                {   // nobody inside the disc around all poses of this obstacle: it adds exact zeros
+                    const double2 bxy = lds2(a_ebd + 32u * k);
+                    const double R2 = lds1(a_ebd + 32u * k + 16u);
+                    bool near = false;
 #pragma unroll
-                for (int q = 0; q < CE; q++) {
-                    const bool valid = (k0 + q) < Nd;
-                    const int k = valid ? k0 + q : k0;
-#pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        const uint32_t ae = a_ell + 48u * (k * N + (act[j] ? tix[j] : 0));
-                        const double2 exy = lds2(ae), csa = lds2(ae + 16u), ir = lds2(ae + 32u);
-                        const double dx = X[j] - exy.x, dy = Y[j] - exy.y;
-                        eca[q][j] = csa.x;
-                        esa[q][j] = csa.y;
-                        const double ea = fma(dx, csa.x, dy * csa.y);
-                        const double eb = fma(dx, csa.y, -(dy * csa.x));
-                        const double hh = fma(-(eb * eb), ir.y, fma(-(ea * ea), ir.x, 1.0));
-                        h[q][j] = valid ? hh : -1.0;
-                        ta[q][j] = ea * ir.x;
-                        tb[q][j] = eb * ir.y;
+                    for (int s = 0; s < S; s++) {
+                        const double dx = X[s] - bxy.x, dy = Y[s] - bxy.y;
+                        near = near || (act[s] && fma(dx, dx, dy * dy) < R2);
                     }
+                    if (!__any_sync(FULL, near)) continue;
                 }
+                double hp[S], ta[S], tb[S], eca[S], esa[S];
+                bool any = false;
 #pragma unroll
-                for (int q = 0; q < CE; q++)
+                for (int s = 0; s < S; s++) {
+                    const uint32_t ae = a_ell + 48u * (k * N + (act[s] ? tix[s] : 0));
+                    const double2 exy = lds2(ae), csa = lds2(ae + 16u), ir = lds2(ae + 32u);
+                    const double dx = X[s] - exy.x, dy = Y[s] - exy.y;
+                    eca[s] = csa.x;
+                    esa[s] = csa.y;
+                    const double ea = fma(dx, csa.x, dy * csa.y);
+                    const double eb = fma(dx, csa.y, -(dy * csa.x));
+                    const double hh = fma(-(eb * eb), ir.y, fma(-(ea * ea), ir.x, 1.0));
+                    const bool in = act[s] && hh > 0.0;
+                    hp[s] = in ? hh : 0.0;
+                    any = any || in;
+                    ta[s] = ea * ir.x;
+                    tb[s] = eb * ir.y;
+                }
+                if (__any_sync(FULL, any)) {
+                    double g = hp[0];
 #pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        m[q][j] = __ballot_sync(FULL, act[j] && h[q][j] > 0.0);
-                        any |= m[q][j];
-                    }
-                if (any) {
+                    for (int s = 1; s < S; s++) g = g + hp[s];
+                    g = gsum<G>(g);
+                    if (F2g && lane == 0 && g > 0.0) F2g[cfg.Nobs + k] = g;
+                    pen = fma(g, g, pen);
+                    const double cg = pn.c * g;
 #pragma unroll
-                    for (int q = 0; q < CE; q++) {
-                        unsigned anyq = 0;
-#pragma unroll
-                        for (int j = 0; j < P; j++) anyq |= m[q][j];
-                        if (anyq) {
-                            const double g = ordered_sum(h[q], m[q]);
-                            if (F2g && lane == 0) F2g[cfg.Nobs + k0 + q] = g;
-                            pen = fma(g, g, pen);
-                            if (GRAD && g > 0.0) {
-                                const double cg = pn.c * g;
-#pragma unroll
-                                for (int j = 0; j < P; j++)
-                                    if (act[j] && h[q][j] > 0.0) {
-                                        double hX = -2.0 * fma(ta[q][j], eca[q][j], tb[q][j] * esa[q][j]);
-                                        double hY = -2.0 * fma(ta[q][j], esa[q][j], -(tb[q][j] * eca[q][j]));
-                                        gX[j] = fma(cg, hX, gX[j]);
-                                        gY[j] = fma(cg, hY, gY[j]);
-                                    }
-                            }
+                    for (int s = 0; s < S; s++)
+                        if (hp[s] > 0.0) {
+                            const double hX = -2.0 * fma(ta[s], eca[s], tb[s] * esa[s]);
+                            const double hY = -2.0 * fma(ta[s], esa[s], -(tb[s] * eca[s]));
+                            gX[s] = fma(cg, hX, gX[s]);
+                            gY[s] = fma(cg, hY, gY[s]);
                         }
-                    }
                 }
             }
         }
         pen_out = pen;
         PROF_MARK(3);
-        if (mode == MODE_F2) return 0.0;
 
-        // stage cost, acceleration cost, ALM term
+        // ---- stage cost (:84-86), acceleration cost and ALM term (:157-171)
         const double inv_ts = hdr(H_INVTS);
         const double xref = hdr(H_XREF), yref = hdr(H_YREF), thref = hdr(H_THREF);
         const double w_rv = hdr(H_RV), w_rw = hdr(H_RW), w_qv = hdr(H_QV), w_q = hdr(H_Q), w_qth = hdr(H_QTH);
         const double w_ap = hdr(H_AP), w_wp = hdr(H_WP), w_qN = hdr(H_QN), w_qthN = hdr(H_QTHN);
-        double cl[P], Aa[P], Aw[P], vref[P];
+        double cl[S], Aa[S], Aw[S], vref[S];
+        {
+            double vp0, wp0;
+            prev_controls(uv, vp0, wp0);
 #pragma unroll
-        for (int j = 0; j < P; j++) {
-            const double v = uv[j].x, w = uv[j].y;
-            double vp, wp_;
-            prev_controls(uv, j, vp, wp_);
-            double c0 = w_rv * (v * v);
-            c0 = fma(w_rw, w * w, c0);
-            vref[j] = act[j] ? lds1(a_vref + 8u * tix[j]) : 0.0;
-            double dv = v - vref[j];
-            c0 = fma(w_qv, dv * dv, c0);
-            double ex = xpre[j] - xref, ey = ypre[j] - yref, et = thpre[j] - thref;
-            c0 = fma(w_q, fma(ex, ex, ey * ey), c0);
-            c0 = fma(w_qth, et * et, c0);
-            c0 = fma(qcte, mind2[j], c0);
-            double acc = (v - vp) * inv_ts, aac = (w - wp_) * inv_ts;
-            c0 = fma(w_ap, acc * acc, c0);
-            c0 = fma(w_wp, aac * aac, c0);
-            double za = fma(yl[j].x, pn.inv_c, acc), zw = fma(yl[j].y, pn.inv_c, aac);
-            double da = sel_excess(za, cfg.lin_acc_min, cfg.lin_acc_max);
-            double dw = sel_excess(zw, -cfg.ang_acc_max, cfg.ang_acc_max);
-            c0 = fma(pn.hc, fma(da, da, dw * dw), c0);
-            cl[j] = act[j] ? c0 : 0.0;
-            Aa[j] = act[j] ? fma(pn.c, da, (2.0 * w_ap) * acc) * inv_ts : 0.0;
-            Aw[j] = act[j] ? fma(pn.c, dw, (2.0 * w_wp) * aac) * inv_ts : 0.0;
-        }
-        // terminal cost at t = N-1
-        const int lN = (N - 1) & 31, jN = (N - 1) >> 5;
-        double XN = 0.0, YN = 0.0, TN = 0.0;
-#pragma unroll
-        for (int j = 0; j < P; j++)
-            if (j == jN) {
-                XN = __shfl_sync(FULL, X[j], lN);
-                YN = __shfl_sync(FULL, Y[j], lN);
-                TN = __shfl_sync(FULL, TH[j], lN);
+            for (int s = 0; s < S; s++) {
+                const double v = uv[s].x, w = uv[s].y;
+                const double vp = (s == 0) ? vp0 : uv[s > 0 ? s - 1 : 0].x, wp_ = (s == 0) ? wp0 : uv[s > 0 ? s - 1 : 0].y;
+                const double2 yl = lds2(la + V_YL * vstride + 16u * G * s);
+                double c0 = w_rv * (v * v);
+                c0 = fma(w_rw, w * w, c0);
+                vref[s] = lds1(a_vref + 8u * tix[s]);
+                const double dv = v - vref[s];
+                c0 = fma(w_qv, dv * dv, c0);
+                const double ex = ((s == 0) ? xp0 : X[s > 0 ? s - 1 : 0]) - xref, ey = ((s == 0) ? yp0 : Y[s > 0 ? s - 1 : 0]) - yref;
+                const double et = ((s == 0) ? thp0 : TH[s > 0 ? s - 1 : 0]) - thref;
+                c0 = fma(w_q, fma(ex, ex, ey * ey), c0);
+                c0 = fma(w_qth, et * et, c0);
+                c0 = fma(qcte, mind2[s], c0);
+                const double acc = (v - vp) * inv_ts, aac = (w - wp_) * inv_ts;
+                c0 = fma(w_ap, acc * acc, c0);
+                c0 = fma(w_wp, aac * aac, c0);
+                const double za = fma(yl.x, pn.inv_c, acc), zw = fma(yl.y, pn.inv_c, aac);
+                const double da = sel_excess(za, cfg.lin_acc_min, cfg.lin_acc_max);
+                const double dw = sel_excess(zw, -cfg.ang_acc_max, cfg.ang_acc_max);
+                c0 = fma(pn.hc, fma(da, da, dw * dw), c0);
+                cl[s] = act[s] ? c0 : 0.0;
+                Aa[s] = act[s] ? fma(pn.c, da, (2.0 * w_ap) * acc) * inv_ts : 0.0;
+                Aw[s] = act[s] ? fma(pn.c, dw, (2.0 * w_wp) * aac) * inv_ts : 0.0;
             }
+        }
+        // terminal cost at t = N-1 (:148)
+        const int glN = (N - 1) / S, sN = (N - 1) - glN * S;
+        double XN = X[0], YN = Y[0], TN = TH[0];
+#pragma unroll
+        for (int s = 1; s < S; s++)
+            if (s == sN) {
+                XN = X[s];
+                YN = Y[s];
+                TN = TH[s];
+            }
+        XN = __shfl_sync(FULL, XN, glN, G);
+        YN = __shfl_sync(FULL, YN, glN, G);
+        TN = __shfl_sync(FULL, TN, glN, G);
         const double eXN = XN - xref, eYN = YN - yref, eTN = TN - thref;
         const double term = fma(w_qN, fma(eXN, eXN, eYN * eYN), w_qthN * (eTN * eTN));
-        if (!GRAD) {
-            const double psi0 = fma(pn.hc, pen, hsum<P>(cl) + term);
-            PROF_MARK(4);
-            return psi0;
-        }
 
-        // backward sweep
-        double mth[P];
+        // ---- backward sweep: position adjoints are suffix sums; the cost sum rides in the same shuffle stages
+        double mth[S];
 #pragma unroll
-        for (int j = 0; j < P; j++) {
-            const bool last = !(tix[j] + 1 < N);
+        for (int s = 0; s < S; s++) {
+            const bool last = !(tix[s] + 1 < N);
             const double qq = last ? w_qN : w_q, qt = last ? w_qthN : w_qth;
-            gX[j] = act[j] ? fma(2.0 * qq, X[j] - xref, gX[j]) : 0.0;
-            gY[j] = act[j] ? fma(2.0 * qq, Y[j] - yref, gY[j]) : 0.0;
-            mth[j] = act[j] ? (2.0 * qt) * (TH[j] - thref) : 0.0;
+            gX[s] = act[s] ? fma(2.0 * qq, X[s] - xref, gX[s]) : 0.0;
+            gY[s] = act[s] ? fma(2.0 * qq, Y[s] - yref, gY[s]) : 0.0;
+            mth[s] = act[s] ? (2.0 * qt) * (TH[s] - thref) : 0.0;
         }
-        double LX[P], LY[P], csum;
-        suffix_scan2_hsum<P>(gX, gY, LX, LY, cl, csum, lane);  // position adjoints + the cost sum
+        double LX[S], LY[S], csum = cl[0];
+#pragma unroll
+        for (int s = 1; s < S; s++) csum = csum + cl[s];
+        {
+            double dXs[S], dYs[S];
+#pragma unroll
+            for (int s = S - 1; s >= 0; s--) {
+                dXs[s] = (s == S - 1) ? gX[s] : dXs[s < S - 1 ? s + 1 : s] + gX[s];
+                dYs[s] = (s == S - 1) ? gY[s] : dYs[s < S - 1 ? s + 1 : s] + gY[s];
+            }
+            double EX, EY;
+            gscan_down_excl2_sum<G>(dXs[0], dYs[0], gl, EX, EY, csum);
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                LX[s] = EX + dXs[s];
+                LY[s] = EY + dYs[s];
+            }
+        }
         const double psi = fma(pn.hc, pen, csum + term);
         PROF_MARK(4);
-        double nn[P], rr[P], TT[P];
+        double nn[S], TT[S];
 #pragma unroll
-        for (int j = 0; j < P; j++) nn[j] = act[j] ? (ts * uv[j].x) * fma(cs[j], LY[j], -(sn[j] * LX[j])) : 0.0;
+        for (int s = 0; s < S; s++) nn[s] = act[s] ? (ts * uv[s].x) * fma(cs[s], LY[s], -(sn[s] * LX[s])) : 0.0;
+        {
+            double nnx = __shfl_down_sync(FULL, nn[0], 1, G);  // the next lane's first step
+            if (gl == G - 1) nnx = 0.0;
+            double dT[S];
 #pragma unroll
-        for (int j = 0; j < P; j++) {
-            double nx = __shfl_down_sync(FULL, nn[j], 1);
-            if (j + 1 < P) {
-                double n0 = __shfl_sync(FULL, nn[(j + 1 < P) ? j + 1 : j], 0);
-                if (lane == 31) nx = n0;
-            } else if (lane == 31) nx = 0.0;
-            rr[j] = act[j] ? mth[j] + nx : 0.0;
-        }
-        suffix_scan<P>(rr, TT, lane);
-#pragma unroll
-        for (int j = 0; j < P; j++) {
-            const double v = uv[j].x, w = uv[j].y;
-            double An = __shfl_down_sync(FULL, Aa[j], 1), Wn = __shfl_down_sync(FULL, Aw[j], 1);
-            if (j + 1 < P) {
-                double A0 = __shfl_sync(FULL, Aa[(j + 1 < P) ? j + 1 : j], 0), W0 = __shfl_sync(FULL, Aw[(j + 1 < P) ? j + 1 : j], 0);
-                if (lane == 31) {
-                    An = A0;
-                    Wn = W0;
-                }
-            } else if (lane == 31) {
-                An = 0.0;
-                Wn = 0.0;
+            for (int s = S - 1; s >= 0; s--) {
+                const double nx = (s == S - 1) ? nnx : nn[s < S - 1 ? s + 1 : s];
+                const double rr = act[s] ? mth[s] + nx : 0.0;
+                dT[s] = (s == S - 1) ? rr : dT[s < S - 1 ? s + 1 : s] + rr;
             }
-            double lv = fma(2.0 * w_rv, v, (2.0 * w_qv) * (v - vref[j])) + (Aa[j] - An);
-            double lw = (2.0 * w_rw) * w + (Aw[j] - Wn);
-            double gv = fma(ts, fma(cs[j], LX[j], sn[j] * LY[j]), lv);
-            double gw = fma(ts, TT[j], lw);
-            gout[j] = act[j] ? make_double2(gv, gw) : make_double2(0.0, 0.0);
+            const double ET = gscan_down_excl<G>(dT[0], gl);
+#pragma unroll
+            for (int s = 0; s < S; s++) TT[s] = ET + dT[s];
+        }
+        {
+            double Anx = __shfl_down_sync(FULL, Aa[0], 1, G), Wnx = __shfl_down_sync(FULL, Aw[0], 1, G);
+            if (gl == G - 1) {
+                Anx = 0.0;
+                Wnx = 0.0;
+            }
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const double v = uv[s].x, w = uv[s].y;
+                const double An = (s == S - 1) ? Anx : Aa[s < S - 1 ? s + 1 : s], Wn = (s == S - 1) ? Wnx : Aw[s < S - 1 ? s + 1 : s];
+                const double lv = fma(2.0 * w_rv, v, (2.0 * w_qv) * (v - vref[s])) + (Aa[s] - An);
+                const double lw = (2.0 * w_rw) * w + (Aw[s] - Wn);
+                const double gv = fma(ts, fma(cs[s], LX[s], sn[s] * LY[s]), lv);
+                const double gw = fma(ts, TT[s], lw);
+                gout[s] = act[s] ? make_double2(gv, gw) : make_double2(0.0, 0.0);
+            }
         }
         PROF_MARK(5);
         return psi;
@@ -978,35 +824,29 @@ struct Warp {
 
 // ---------------------------------------------------------------------------------
 // The solver: ALM/PM outer loop around PANOC as a phase machine with one evaluation site.
-// Phases that end in an evaluation set (x, mode) and fall through to it; the others `continue`.
-enum Phase {
-    PH_OUTER_BEGIN, PH_INIT_A, PH_INIT_B, PH_STEP_BEGIN, PH_LIP, PH_COST_U, PH_LIP_LOOP, PH_LIP_RETRY, PH_IT0, PH_LS,
-    PH_STEP_DONE, PH_SOLVE_END, PH_F2, PH_FINAL, PH_EXIT, PH_HELP_WAIT, PH_HELP_EVAL
-};
+// Phases that end in an evaluation set x (per group) and fall through to it; the others `continue`.
+enum Phase { PH_OUTER_BEGIN, PH_INIT, PH_STEP_BEGIN, PH_A, PH_RETRY, PH_LS, PH_STEP_DONE, PH_SOLVE_END, PH_F2, PH_EXIT };
 
-// Owner mode (helper == false) solves the staged problem.  Helper mode (entered once the problem queue is empty)
-// serves the other warps of the CTA: it polls their job records for posted line-search trials
-// x = u - (1-tau) fpr - tau dir, evaluates them in the owner's arena through the same evaluation site and writes
-// back psi, the gradient and the trial's envelope value; it returns when no warp of the CTA owns a problem any
-// more.  Who evaluates a trial never changes its bits, so results do not depend on timing.
-// HC (latency mode, chosen by the host for batches of at most two problems per SM): psi(uhalf) of every
-// iteration is also handed to a helper while the owner runs the L-BFGS update and the two-loop recursion: a lone
-// problem's iteration drops from 29.5k to 23k cycles, but the extra code costs 3-6 % on full batches, hence two
-// instantiations.
-template <int P, int NF, bool HC>
-__device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], nmpc_stats& st_out, const bool helper,
-                             const uint32_t a_live, const int nwarps, long long* prof_out = nullptr) {
+__device__ __forceinline__ unsigned long long nm_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int G, int S>
+__device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out, long long* prof_out = nullptr) {
+    constexpr int NG = 32 / G;
 #ifdef NMPC_PROFILE
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long tstart = clock64();
 #endif
     const nmpc_config& cfg = W.cfg;
-    const int lane = W.lane;
+    const int lane = W.lane, grp = W.grp;
     const int mem = cfg.lbfgs_memory, mem1 = cfg.lbfgs_memory + 1;
     const int nf2 = cfg.Nobs + cfg.Ndynobs;
     // warp-uniform state
-    double gamma = 0.0, inv_gamma = 0.0, sigma = 0.0, cost = 0.0, norm_fpr = 0.0, tau = 1.0;
-    double cost_half = 0.0, rhs_ls = 0.0, lb_gamma = 1.0;
+    double gamma = 0.0, inv_gamma = 0.0, sigma = 0.0, cost = 0.0, norm_fpr = 0.0;
+    double rhs_ls = 0.0, lb_gamma = 1.0, fbe_u = 0.0, ip = 0.0;
     // rarely touched warp-uniform scalars live in the arena header: every lane stores the same value and
     // reads back its own store, so no synchronisation is involved
     auto sget = [&](int i) { return lds1(W.a_hdr + 8u * i); };
@@ -1018,53 +858,129 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
     sput(H_DYNP, 0.0);
     sput(H_LIP, 0.0);
     Pen pn = make_pen(cfg.initial_penalty);
-    Pen pn_eval = pn;
     int iteration = 0, n_cost = 0, n_grad = 0, lb_active = 0, lb_first = 1, lb_head = 0;
     int alm_iter = 0, inner_total = 0, num_outer = 0, status = NMPC_CONVERGED, inner_status = NMPC_CONVERGED;
-    int num_iter = 0, it_lip = 0, nls = 0;
-    bool cont = true, fbe_valid = false;
-    double fbe_u = 0.0;
+    int num_iter = 0, it_lip = 0, e0 = 0, gfirst = 0;
+    bool cont = true, fbe_valid = false, timed_out = false;
     const double inv_ts = W.hdr(H_INVTS);
-    bool cost_pending = false;  // psi(uhalf) of this iteration is being evaluated by a helper warp
-    bool spec_done = false;     // L-BFGS update and direction of this iteration are already done (speculatively)
-    int ls_hint = 0;  // trials the previous line search needed beyond tau = 1
-    int ls_seq = 0;   // owner: line searches started (tags job records); helper: slot r of the job being served
+    const unsigned long long t_begin = cfg.max_duration_micros > 0 ? nm_globaltimer() : 0ull;
+    const unsigned long long t_budget = (unsigned long long)(cfg.max_duration_micros > 0 ? cfg.max_duration_micros : 0) * 1000ull;
 
-    double2 x[P], g[P];  // evaluation point / gradient out
+    double2 x[S], g[S];  // this group's evaluation point / gradient out
     double pen = 0.0;
-    int mode = MODE_GRAD;
-    int phase = helper ? PH_HELP_WAIT : PH_OUTER_BEGIN;
+    Pen pn_eval = pn;
+    int phase = PH_OUTER_BEGIN;
 
     auto set_gamma = [&](double gm) {  // sigma only changes with gamma: computed here, not once per iteration
         gamma = gm;
         inv_gamma = 1.0 / gm;
         sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * gm);
     };
-    // gradient_step() + half_step(): gstep = p - gamma*grad ; uhalf = Proj_U(gstep); both stored
-    auto grad_step_half = [&](const double2(&p)[P], const double2(&gr)[P], double2(&gs)[P], double2(&uh)[P]) {
+    // gradient_step() + half_step(): gs = p - gamma*grad ; uh = Proj_U(gs)
+    auto grad_step_half = [&](const double2(&p)[S], const double2(&gr)[S], double2(&gs)[S], double2(&uh)[S]) {
 #pragma unroll
-        for (int j = 0; j < P; j++) {
-            gs[j].x = fma(-gamma, gr[j].x, p[j].x);
-            gs[j].y = fma(-gamma, gr[j].y, p[j].y);
-            uh[j].x = W.act[j] ? clampd(gs[j].x, cfg.lin_vel_min, cfg.lin_vel_max) : 0.0;
-            uh[j].y = W.act[j] ? clampd(gs[j].y, -cfg.ang_vel_max, cfg.ang_vel_max) : 0.0;
+        for (int s = 0; s < S; s++) {
+            gs[s].x = fma(-gamma, gr[s].x, p[s].x);
+            gs[s].y = fma(-gamma, gr[s].y, p[s].y);
+            uh[s].x = W.act[s] ? clampd(gs[s].x, cfg.lin_vel_min, cfg.lin_vel_max) : 0.0;
+            uh[s].y = W.act[s] ? clampd(gs[s].y, -cfg.ang_vel_max, cfg.ang_vel_max) : 0.0;
         }
-        W.st(V_GSTEP, gs);
-        W.st(V_UHALF, uh);
     };
-    auto compute_fpr = [&](const double2(&uh)[P], double2(&fpr)[P]) {
-        double e[P];
+    // per-lane partials (serial over the lane's steps), then the group sum
+    auto dot = [&](const double2(&a)[S], const double2(&b)[S]) {
+        double e = fma(a[0].y, b[0].y, a[0].x * b[0].x);
 #pragma unroll
-        for (int j = 0; j < P; j++) {
-            double d0 = u[j].x - uh[j].x, d1 = u[j].y - uh[j].y;
-            fpr[j] = make_double2(d0, d1);
-            e[j] = fma(d1, d1, d0 * d0);
+        for (int s = 1; s < S; s++) e = e + fma(a[s].y, b[s].y, a[s].x * b[s].x);
+        return e;
+    };
+    auto diff2 = [&](const double2(&a)[S], const double2(&b)[S]) {
+        double e = 0.0;
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const double d0 = a[s].x - b[s].x, d1 = a[s].y - b[s].y;
+            const double t = fma(d1, d1, d0 * d0);
+            e = (s == 0) ? t : e + t;
         }
-        norm_fpr = sqrt(hsum<P>(e));
+        return e;
+    };
+    auto compute_fpr = [&](const double2(&uh)[S], double2(&fpr)[S]) {
+#pragma unroll
+        for (int s = 0; s < S; s++) fpr[s] = make_double2(u[s].x - uh[s].x, u[s].y - uh[s].y);
+        norm_fpr = sqrt(gsum<G>(dot(fpr, fpr)));
     };
     auto slot = [&](int i) {
-        int s = lb_head + i;
-        return (s >= mem1) ? s - mem1 : s;
+        int sl = lb_head + i;
+        return (sl >= mem1) ? sl - mem1 : sl;
+    };
+    // Lipschitz test of PANOC's step size (update_lipschitz_constant): true = the step size must be halved
+    auto lip_test_fails = [&](double cost_half) -> bool {
+        const double rhs = cost + LIPSCHITZ_UPDATE_EPSILON * fabs(cost) - ip + (GAMMA_L_COEFF * 0.5 * inv_gamma) * (norm_fpr * norm_fpr);
+        return cost_half > rhs && it_lip < MAX_LIPSCHITZ_UPDATE_ITERATIONS && sget(H_LIP) < MAX_LIPSCHITZ_CONSTANT;
+    };
+    // halve gamma, drop the L-BFGS memory, recompute the half step; every group then evaluates psi(u_half)
+    auto lip_halve = [&]() {
+        lb_active = 0;
+        lb_first = 1;
+        fbe_valid = false;
+        sput(H_LIP, sget(H_LIP) * 2.0);
+        set_gamma(gamma / 2.0);
+        double2 gr[S], gs[S], uh[S];
+        W.ld(V_GRAD, gr);
+        grad_step_half(u, gr, gs, uh);
+        __syncwarp();
+        W.st(V_GSTEP, gs);
+        W.st(V_UHALF, uh);
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < S; s++) x[s] = uh[s];
+        pn_eval = pn;
+        phase = PH_RETRY;
+    };
+    // line-search trial points of a call whose groups hold the exponents e0 + grp - gfirst (tau = 2^-e, at most 2^-10)
+    auto form_trials = [&](const double2(&uh)[S]) {
+        int e = e0 + grp - gfirst;
+        e = e > MAX_LINESEARCH_ITERATIONS ? MAX_LINESEARCH_ITERATIONS : e;
+        // tau = 2^-e exactly (the reference halves tau e times)
+        const double tau = __longlong_as_double((long long)(1023 - (e < 0 ? 0 : e)) << 52);
+        const double om = 1.0 - tau;
+        double2 fpr[S], dir[S];
+        W.ld(V_FPR, fpr);
+        W.ld(V_DIR, dir);
+        const bool is_half = grp < gfirst;  // group 0 of a first call evaluates psi(u_half)
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const double tx = fma(-tau, dir[s].x, fma(-om, fpr[s].x, u[s].x));
+            const double ty = fma(-tau, dir[s].y, fma(-om, fpr[s].y, u[s].y));
+            x[s] = is_half ? uh[s] : make_double2(tx, ty);
+        }
+        pn_eval = pn;
+    };
+    // right-hand side of the line search from the forward-backward envelope at u (compute_rhs_ls)
+    auto rhs_from_envelope = [&]() {
+        double2 gs[S], uh[S], gr[S];
+        W.ld(V_GSTEP, gs);
+        W.ld(V_UHALF, uh);
+        W.ld(V_GRAD, gr);
+        double dist2 = diff2(gs, uh), gg = dot(gr, gr);
+        gsum2<G>(dist2, gg);
+        const double fbe = cost - (0.5 * gamma) * gg + (0.5 * dist2) * inv_gamma;
+        rhs_ls = fbe - sigma * (norm_fpr * norm_fpr);
+    };
+    // update_no_linesearch() of iteration 0: u <- u_half with the cost and gradient group 0 has just evaluated there
+    auto first_iteration_update = [&](double cost_half) {
+        W.st(V_GRAD, g);  // group 0 evaluated u_half
+        __syncwarp();
+        double2 gr[S], gs[S], uh[S];
+        W.ld(V_UHALF, u);
+        W.ld(V_GRAD, gr);
+        cost = cost_half;
+        grad_step_half(u, gr, gs, uh);
+        W.st(V_GSTEP, gs);
+        W.st(V_UHALF, uh);
+        __syncwarp();
+        n_grad++;
+        iteration++;
+        phase = PH_STEP_DONE;
     };
 
 #ifdef NMPC_PROFILE
@@ -1083,147 +999,104 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
 #endif
     for (;;) {
         PH_ACCOUNT(16 + phase);
-        // ------------------------------------------------------------------ pre: pick (x, mode)
+        __syncwarp();  // phases exchange vectors between groups through the arena
+        // ------------------------------------------------------------------ pre: pick this group's x
         switch (phase) {
             case PH_OUTER_BEGIN: {
-                num_outer++;
-#pragma unroll
-                for (int j = 0; j < P; j++) {  // project_on_set_y
-                    yl[j].x = clampd(yl[j].x, -Y_SET_BOUND, Y_SET_BOUND);
-                    yl[j].y = clampd(yl[j].y, -Y_SET_BOUND, Y_SET_BOUND);
+                if (t_budget && nm_globaltimer() - t_begin > t_budget) {  // AlmOptimizer::solve: no time left
+                    status = NMPC_NOT_CONVERGED_OUT_OF_TIME;
+                    phase = PH_EXIT;
+                    continue;
                 }
-                if (NMPC_HELP_R > 0) W.st(V_YL, yl);  // helper warps read the multipliers from the arena
-                // panoc init
+                num_outer++;
+                {
+                    double2 yl[S];
+                    W.ld(V_YL, yl);
+#pragma unroll
+                    for (int s = 0; s < S; s++) {  // project_on_set_y
+                        yl[s].x = clampd(yl[s].x, -Y_SET_BOUND, Y_SET_BOUND);
+                        yl[s].y = clampd(yl[s].y, -Y_SET_BOUND, Y_SET_BOUND);
+                    }
+                    __syncwarp();
+                    W.st(V_YL, yl);
+                }
+                // panoc init: cost and gradient at u (group 0) and the gradient at u + h (the other groups) in one
+                // call; estimate_loc_lip leaves u perturbed by h
                 lb_active = 0;
                 lb_first = 1;
                 fbe_valid = false;
-                tau = 1.0;
                 iteration = 0;
+                {
+                    double e = 0.0;
 #pragma unroll
-                for (int j = 0; j < P; j++) x[j] = u[j];
-                mode = MODE_GRAD;
-                phase = PH_INIT_A;
+                    for (int s = 0; s < S; s++) {
+                        const double ex_ = EPSILON_LIPSCHITZ * u[s].x, ey_ = EPSILON_LIPSCHITZ * u[s].y;
+                        const double hx = W.act[s] ? ((ex_ > DELTA_LIPSCHITZ) ? ex_ : DELTA_LIPSCHITZ) : 0.0;
+                        const double hy = W.act[s] ? ((ey_ > DELTA_LIPSCHITZ) ? ey_ : DELTA_LIPSCHITZ) : 0.0;
+                        const double t = fma(hy, hy, hx * hx);
+                        e = (s == 0) ? t : e + t;
+                        const double2 up = make_double2(u[s].x + hx, u[s].y + hy);
+                        x[s] = (grp == 0) ? u[s] : up;
+                        u[s] = up;
+                    }
+                    sput(H_NORMH, sqrt(gsum<G>(e)));
+                }
+                pn_eval = pn;
+                __syncwarp();
+                phase = PH_INIT;
                 break;
             }
             case PH_STEP_BEGIN: {
-                double2 gr[P], uh[P], fpr[P];
+                double2 gr[S], uh[S], fpr[S];
                 W.ld(V_GRAD, gr);
                 W.ld(V_UHALF, uh);
                 compute_fpr(uh, fpr);
                 bool exit_now = false;
                 if (norm_fpr < cfg.tolerance) {
-                    double e[P];
+                    double e = 0.0;
 #pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        double p0 = iteration ? gr[j].x : 0.0, p1 = iteration ? gr[j].y : 0.0;
-                        double r0 = fma(fpr[j].x, inv_gamma, gr[j].x) - p0;
-                        double r1 = fma(fpr[j].y, inv_gamma, gr[j].y) - p1;
-                        e[j] = fma(r1, r1, r0 * r0);
+                    for (int s = 0; s < S; s++) {
+                        const double p0 = iteration ? gr[s].x : 0.0, p1 = iteration ? gr[s].y : 0.0;
+                        const double r0 = fma(fpr[s].x, inv_gamma, gr[s].x) - p0;
+                        const double r1 = fma(fpr[s].y, inv_gamma, gr[s].y) - p1;
+                        const double t = fma(r1, r1, r0 * r0);
+                        e = (s == 0) ? t : e + t;
                     }
-                    exit_now = sqrt(hsum<P>(e)) < sget(H_AKKT);
+                    exit_now = sqrt(gsum<G>(e)) < sget(H_AKKT);
                 }
                 if (exit_now) {
                     phase = PH_SOLVE_END;
                     continue;
                 }
+                __syncwarp();
                 W.st(V_FPR, fpr);
                 it_lip = 0;
-#if NMPC_HELP_R > 0
-                if constexpr (HC) {
-                // With an idle sub-partition in the CTA, psi(uhalf) (only needed for the Lipschitz test) goes to a
-                // helper warp while this warp already updates the L-BFGS memory and runs the two-loop recursion.
-                // If the test then fails (rare), the update is discarded exactly as the reference discards its memory.
-                // Only in the deep tail (few owners left in the CTA): otherwise the cost jobs take helper time from the
-                // line-search trials of the other owners, which are worth more.
-                if (__builtin_expect(iteration > 0 && ldv_shared(a_live) <= NMPC_HELP_COST_MAXLIVE, 0) &&
-                    __any_sync(FULL, lane < 4 && lane < nwarps && ldv_shared(a_live + 4u + 4u * lane) <= NMPC_HELP_PART_MAX)) {
-                    const uint32_t aj = W.a_job + JOB_BYTES * NMPC_HELP_R;
-                    int posted = 0;
-                    __threadfence_block();
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int stt = ldv_shared(aj);
-                        if (stt == JOB_EMPTY || stt == JOB_DONE) {
-                            stsi(aj + 4u, 0);  // trial 0 = cost evaluation at uhalf
-                            stsi(aj + 8u, ls_seq);
-                            sts1(aj + 16u, gamma);
-                            sts1(aj + 24u, pn.c);
-                            __threadfence_block();
-                            stv_shared(aj, JOB_POSTED);
-                            posted = 1;
-                        }
-                    }
-                    if (__shfl_sync(FULL, posted, 0)) {
-                        cost_pending = true;
-                        phase = PH_LIP_LOOP;
-                        continue;
-                    }
-                }
-                }
-#endif
-#pragma unroll
-                for (int j = 0; j < P; j++) x[j] = uh[j];
-                mode = MODE_COST;
-                phase = PH_LIP;
-                break;
-            }
-            case PH_LIP_LOOP: {
-                double2 gr[P], fpr[P], s[P], y[P];
-                W.ld(V_GRAD, gr);
-                W.ld(V_FPR, fpr);
                 // <grad, fpr> for the Lipschitz test and, when a previous (state, fpr) pair exists, the three
-                // inner products of the L-BFGS update (s.y, s.s, y.y) in ONE interleaved butterfly
-                double ip, ys = 0.0, ss = 0.0, yy = 0.0;
+                // inner products of the L-BFGS update (s.y, s.s, y.y) in ONE interleaved group sum.
+                // The update and the direction are computed BEFORE psi(u_half) is known: if the Lipschitz test then
+                // fails (rare), lip_halve() drops the memory exactly like the reference does before its update.
+                double2 q[S];
                 if (lb_first) {
-                    ip = wdot<P>(gr, fpr);
-                } else {
-                    double2 os[P], og[P];
-                    W.ld(V_OLDS, os);
-                    W.ld(V_OLDG, og);
-                    double e0[P], e1[P], e2[P], e3[P];
-#pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        s[j] = make_double2(u[j].x - os[j].x, u[j].y - os[j].y);
-                        y[j] = make_double2(fpr[j].x - og[j].x, fpr[j].y - og[j].y);
-                        e0[j] = fma(gr[j].y, fpr[j].y, gr[j].x * fpr[j].x);
-                        e1[j] = fma(s[j].y, y[j].y, s[j].x * y[j].x);
-                        e2[j] = fma(s[j].y, s[j].y, s[j].x * s[j].x);
-                        e3[j] = fma(y[j].y, y[j].y, y[j].x * y[j].x);
-                    }
-                    hsum4<P>(e0, e1, e2, e3, ip, ys, ss, yy);
-                }
-                // Lipschitz test of PANOC's step size; on failure: halve gamma, drop the L-BFGS memory, re-evaluate
-                auto lip_test_fails = [&]() -> bool {
-                    const double rhs = cost + LIPSCHITZ_UPDATE_EPSILON * fabs(cost) - ip +
-                                       (GAMMA_L_COEFF * 0.5 * inv_gamma) * (norm_fpr * norm_fpr);
-                    if (!(cost_half > rhs && it_lip < MAX_LIPSCHITZ_UPDATE_ITERATIONS && sget(H_LIP) < MAX_LIPSCHITZ_CONSTANT))
-                        return false;
-                    lb_active = 0;
-                    lb_first = 1;
-                    fbe_valid = false;
-                    spec_done = false;
-                    sput(H_LIP, sget(H_LIP) * 2.0);
-                    set_gamma(gamma / 2.0);
-                    double2 gs[P], uh[P];
-                    grad_step_half(u, gr, gs, uh);
-#pragma unroll
-                    for (int j = 0; j < P; j++) x[j] = uh[j];
-                    mode = MODE_COST;
-                    phase = PH_LIP_RETRY;
-                    return true;
-                };
-                if (!(HC && __builtin_expect(cost_pending, 0)) && lip_test_fails()) break;
-                double2 q[P];
-                if (!(HC && __builtin_expect(spec_done, 0))) {
-                // lbfgs_direction(): update_hessian(g = fpr, state = u)
-                if (lb_first) {
+                    ip = gsum<G>(dot(gr, fpr));
                     lb_first = 0;
                     W.st(V_OLDS, u);
                     W.st(V_OLDG, fpr);
                 } else {
+                    double2 os[S], og[S], sv[S], yv[S];
+                    W.ld(V_OLDS, os);
+                    W.ld(V_OLDG, og);
+#pragma unroll
+                    for (int s = 0; s < S; s++) {
+                        sv[s] = make_double2(u[s].x - os[s].x, u[s].y - os[s].y);
+                        yv[s] = make_double2(fpr[s].x - og[s].x, fpr[s].y - og[s].y);
+                    }
+                    double ys = dot(sv, yv), ss = dot(sv, sv), yy = dot(yv, yv);
+                    ip = dot(gr, fpr);
+                    gsum4<G>(ip, ys, ss, yy);
+                    // lbfgs update_hessian(g = fpr, state = u)
                     const int tmp = slot(mem);
-                    W.st(V_S + tmp, s);
-                    W.st(V_Y + tmp, y);
+                    W.st(V_S + tmp, sv);
+                    W.st(V_Y + tmp, yv);
                     const double rho_new = 1.0 / ys;
                     bool accept = !(ss <= DBL_EPS || ys <= SY_EPSILON);
                     if (accept) {
@@ -1234,19 +1107,20 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                     if (accept) {
                         W.st(V_OLDS, u);
                         W.st(V_OLDG, fpr);
-                        if (lane == 0) sts1(W.a_rho + 8u * tmp, rho_new);
+                        sts1_if(W.a_rho + 8u * tmp, rho_new, lane == 0);
                         lb_head = (lb_head + mem >= mem1) ? lb_head + mem - mem1 : lb_head + mem;
                         lb_gamma = (1.0 / rho_new) / yy;
                         lb_active = (lb_active + 1 < mem) ? lb_active + 1 : mem;
-                        __syncwarp();
                     }
                 }
-                if (iteration == 0) {  // update_no_linesearch(): u <- uhalf
-                    W.ld(V_UHALF, u);
+                __syncwarp();
+                if (iteration == 0) {
+                    // group 0: psi and grad psi at u_half (Lipschitz test, then update_no_linesearch);
+                    // the other groups: psi(u) — u was perturbed by the Lipschitz estimate, its cost is stale
 #pragma unroll
-                    for (int j = 0; j < P; j++) x[j] = u[j];
-                    mode = MODE_GRAD;
-                    phase = PH_IT0;
+                    for (int s = 0; s < S; s++) x[s] = (grp == 0) ? uh[s] : u[s];
+                    pn_eval = pn;
+                    phase = PH_A;
                     break;
                 }
                 // direction = H * fpr (two-loop recursion)
@@ -1254,156 +1128,97 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 const long long tl0 = clock64();
 #endif
 #pragma unroll
-                for (int j = 0; j < P; j++) q[j] = fpr[j];
+                for (int s = 0; s < S; s++) q[s] = fpr[s];
                 if (lb_active > 0) {
-                    // each step's (s, y) pair is fetched while the previous step's butterfly is in flight
-                    double2 sv[P], yv[P], sn[P], yn[P];
-                    int sl = slot(0);
-                    W.ld(V_S + sl, sv);
-                    W.ld(V_Y + sl, yv);
-                    double rho = lds1(W.a_rho + 8u * sl);
-                    NMPC_NOUNROLL
-                    for (int k = 0; k < lb_active; k++) {
-                        const int sl_n = slot((k + 1 < lb_active) ? k + 1 : k);
-                        W.ld(V_S + sl_n, sn);
-                        W.ld(V_Y + sl_n, yn);
-                        const double rho_n = lds1(W.a_rho + 8u * sl_n);
-                        const double al = rho * wdot<P>(sv, q);
-                        if (lane == 0) sts1(W.a_alpha + 8u * k, al);
+                    // alpha_k = rho_k <s_k, q>; q -= alpha_k y_k  (k = 0 newest).  The pair of the NEXT step is fetched
+                    // while this step's group sum is in flight; two steps per trip so the prefetch needs no moves.
+                    const uint32_t a_s0 = W.la + V_S * W.vstride, a_y0 = W.la + V_Y * W.vstride;
+                    auto ldv = [&](uint32_t base, int sl, double2(&r)[S]) {
 #pragma unroll
-                        for (int j = 0; j < P; j++) {
-                            q[j].x = fma(-al, yv[j].x, q[j].x);
-                            q[j].y = fma(-al, yv[j].y, q[j].y);
-                            sv[j] = sn[j];
-                            yv[j] = yn[j];
+                        for (int s = 0; s < S; s++) r[s] = lds2(base + sl * W.vstride + 16u * G * s);
+                    };
+                    auto fwd = [&](int k, const double2(&sv)[S], const double2(&yv)[S], double rho) {
+                        const double al = rho * gsum<G>(dot(sv, q));
+                        sts1_if(W.a_alpha + 8u * k, al, lane == 0);
+#pragma unroll
+                        for (int s = 0; s < S; s++) {
+                            q[s].x = fma(-al, yv[s].x, q[s].x);
+                            q[s].y = fma(-al, yv[s].y, q[s].y);
                         }
-                        rho = rho_n;
+                    };
+                    auto bwd = [&](int k, const double2(&sv)[S], const double2(&yv)[S], double rho) {
+                        const double alk = lds1(W.a_alpha + 8u * k);
+                        const double beta = rho * gsum<G>(dot(yv, q));
+                        const double co = alk - beta;
+#pragma unroll
+                        for (int s = 0; s < S; s++) {
+                            q[s].x = fma(co, sv[s].x, q[s].x);
+                            q[s].y = fma(co, sv[s].y, q[s].y);
+                        }
+                    };
+                    double2 sa[S], ya[S], sb[S], yb[S];
+                    double rhoa, rhob = 0.0;
+                    int sl = lb_head;  // physical slot of pair k; k + 1 is the next slot of the ring
+                    ldv(a_s0, sl, sa);
+                    ldv(a_y0, sl, ya);
+                    rhoa = lds1(W.a_rho + 8u * sl);
+                    int k = 0;
+#pragma unroll 1
+                    for (; k + 1 < lb_active; k += 2) {
+                        sl = (sl + 1 >= mem1) ? 0 : sl + 1;
+                        ldv(a_s0, sl, sb);
+                        ldv(a_y0, sl, yb);
+                        rhob = lds1(W.a_rho + 8u * sl);
+                        fwd(k, sa, ya, rhoa);
+                        sl = (sl + 1 >= mem1) ? 0 : sl + 1;
+                        ldv(a_s0, sl, sa);  // (one pair past the end on the last trip: a valid slot, never used)
+                        ldv(a_y0, sl, ya);
+                        rhoa = lds1(W.a_rho + 8u * sl);
+                        fwd(k + 1, sb, yb, rhob);
+                    }
+                    if (k < lb_active) {  // odd count: pair k is in (sa, ya)
+                        fwd(k, sa, ya, rhoa);
+                        k++;
+                    } else {  // even count: (sa, ya) hold the pair past the end; the newest processed pair is (sb, yb)
+                        sl = (sl == 0) ? mem1 - 1 : sl - 1;
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        q[j].x = q[j].x * lb_gamma;
-                        q[j].y = q[j].y * lb_gamma;
+                    for (int s = 0; s < S; s++) {
+                        q[s].x = q[s].x * lb_gamma;
+                        q[s].y = q[s].y * lb_gamma;
                     }
-                    // (sv, yv, rho) now hold the newest pair (k = lb_active-1): the backward loop starts there
-                    NMPC_NOUNROLL
-                    for (int k = lb_active - 1; k >= 0; k--) {
-                        const int sl_n = slot((k > 0) ? k - 1 : 0);
-                        W.ld(V_S + sl_n, sn);
-                        W.ld(V_Y + sl_n, yn);
-                        const double rho_n = lds1(W.a_rho + 8u * sl_n);
-                        const double alk = lds1(W.a_alpha + 8u * k);
-                        const double beta = rho * wdot<P>(yv, q);
-                        const double co = alk - beta;
-#pragma unroll
-                        for (int j = 0; j < P; j++) {
-                            q[j].x = fma(co, sv[j].x, q[j].x);
-                            q[j].y = fma(co, sv[j].y, q[j].y);
-                            sv[j] = sn[j];
-                            yv[j] = yn[j];
-                        }
-                        rho = rho_n;
+                    // backward: k = lb_active-1 .. 0, sl = slot of pair lb_active-1
+                    ldv(a_s0, sl, sa);
+                    ldv(a_y0, sl, ya);
+                    rhoa = lds1(W.a_rho + 8u * sl);
+                    k = lb_active - 1;
+#pragma unroll 1
+                    for (; k >= 1; k -= 2) {
+                        sl = (sl == 0) ? mem1 - 1 : sl - 1;
+                        ldv(a_s0, sl, sb);
+                        ldv(a_y0, sl, yb);
+                        rhob = lds1(W.a_rho + 8u * sl);
+                        bwd(k, sa, ya, rhoa);
+                        sl = (sl == 0) ? mem1 - 1 : sl - 1;
+                        ldv(a_s0, sl, sa);
+                        ldv(a_y0, sl, ya);
+                        rhoa = lds1(W.a_rho + 8u * sl);
+                        bwd(k - 1, sb, yb, rhob);
                     }
+                    if (k == 0) bwd(0, sa, ya, rhoa);
                 }
                 W.st(V_DIR, q);
+                __syncwarp();
 #ifdef NMPC_PROFILE
                 prof[4] += clock64() - tl0;
                 prof[5]++;
 #endif
-                } else {  // update and direction were done before psi(uhalf) was known
-                    W.ld(V_DIR, q);
-                    spec_done = false;
-                }
-#if NMPC_HELP_R > 0
-                if constexpr (HC) if (__builtin_expect(cost_pending, 0)) {
-                    cost_pending = false;
-                    const uint32_t aj = W.a_job + JOB_BYTES * NMPC_HELP_R;
-                    int got = 0;
-                    if (lane == 0) {
-                        int stt = ldv_shared(aj);
-                        if (stt == JOB_POSTED && cas_shared(aj, JOB_POSTED, JOB_EMPTY) == JOB_POSTED) stt = JOB_EMPTY;
-                        if (stt != JOB_EMPTY) {
-                            while (ldv_shared(aj) != JOB_DONE) __nanosleep(20);
-                            got = 1;
-                        }
-                    }
-                    got = __shfl_sync(FULL, got, 0);
-                    if (!got) {  // no helper picked it up: evaluate here and come back (update / direction are kept)
-                        spec_done = true;
-                        W.ld(V_UHALF, x);
-                        mode = MODE_COST;
-                        phase = PH_LIP;
-                        break;
-                    }
-                    __threadfence_block();
-                    cost_half = lds1(aj + 32u);
-                    n_cost += 2;  // the evaluation and OpEn's re-evaluation of psi(u) (see PH_LIP)
-                    __syncwarp();
-                    if (lane == 0) stv_shared(aj, JOB_EMPTY);
-                    if (lip_test_fails()) break;
-                }
-#endif
-                // linesearch(): right-hand side on the forward-backward envelope
-                if (fbe_valid) {
-                    // the envelope at u is the accepted trial's left-hand side of the previous line search
-                    // (same cost, gradient, gamma and stored gstep/uhalf: bit-identical), unless gamma changed
-                    rhs_ls = fbe_u - sigma * (norm_fpr * norm_fpr);
-                } else {
-                    double2 gs[P], uh[P];
-                    W.ld(V_GSTEP, gs);
-                    W.ld(V_UHALF, uh);
-                    double dist2, gg;
-                    {
-                        double e[P], f[P];
-#pragma unroll
-                        for (int j = 0; j < P; j++) {
-                            double d0 = gs[j].x - uh[j].x, d1 = gs[j].y - uh[j].y;
-                            e[j] = fma(d1, d1, d0 * d0);
-                            f[j] = fma(gr[j].y, gr[j].y, gr[j].x * gr[j].x);
-                        }
-                        hsum2<P>(e, f, dist2, gg);
-                    }
-                    const double fbe = cost - (0.5 * gamma) * gg + (0.5 * dist2) * inv_gamma;
-                    rhs_ls = fbe - sigma * (norm_fpr * norm_fpr);
-                }
-                tau = 1.0;
-                nls = 0;
-#if NMPC_HELP_R > 0
-                ls_seq++;
-                // a_live[0]: warps of the CTA in owner mode; a_live[1..4]: the same per SM sub-partition (warp % 4).
-                // Helpers only work from a sub-partition without owners, so they never take issue slots or FP64
-                // pipe cycles from a warp that is solving a problem.
-                const bool idle_part = __any_sync(FULL, lane < 4 && lane < nwarps && ldv_shared(a_live + 4u + 4u * lane) <= NMPC_HELP_PART_MAX);
-                if (idle_part) {
-                    // offer the next trials (tau = 1/2, 1/4, ...) while this warp evaluates tau = 1.
-                    // A record still held by a late helper of an earlier search is skipped.
-                    W.st(V_U, u);
-                    __threadfence_block();
-                    __syncwarp();
-                    // NMPC_HELP_EXTRA < NMPC_HELP_R would limit the offer to what the previous search needed plus
-                    // EXTRA trials (less speculative work); measured worse than always offering all of them
-                    if (lane < NMPC_HELP_R && lane < ls_hint + NMPC_HELP_EXTRA) {
-                        const uint32_t aj = W.a_job + JOB_BYTES * lane;
-                        const int stt = ldv_shared(aj);
-                        if (stt == JOB_EMPTY || stt == JOB_DONE) {
-                            stsi(aj + 4u, lane + 1);
-                            stsi(aj + 8u, ls_seq);
-                            sts1(aj + 16u, gamma);
-                            sts1(aj + 24u, pn.c);
-                            __threadfence_block();
-                            stv_shared(aj, JOB_POSTED);
-                        }
-                    }
-                    __syncwarp();
-                }
-#endif
-#pragma unroll
-                for (int j = 0; j < P; j++) {  // tau = 1: u - 0*fpr - 1*dir
-                    x[j].x = fma(-tau, q[j].x, fma(-0.0, fpr[j].x, u[j].x));
-                    x[j].y = fma(-tau, q[j].y, fma(-0.0, fpr[j].y, u[j].y));
-                }
-                mode = MODE_GRAD;
-                phase = PH_LS;
+                // ONE call: group 0 evaluates psi(u_half), groups 1.. the trials tau = 1, 1/2, ...
+                e0 = 0;
+                gfirst = 1;
+                form_trials(uh);
+                phase = PH_A;
                 break;
             }
             case PH_STEP_DONE: {
@@ -1413,6 +1228,11 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 }
                 num_iter++;
                 cont = num_iter < cfg.max_inner_iterations;
+                if (t_budget && nm_globaltimer() - t_begin > t_budget) {  // PANOCOptimizer::solve: time ran out
+                    timed_out = true;
+                    phase = PH_SOLVE_END;
+                    continue;
+                }
                 phase = PH_STEP_BEGIN;
                 continue;
             }
@@ -1420,93 +1240,22 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 inner_total += num_iter;
                 bool fin = true;
 #pragma unroll
-                for (int j = 0; j < P; j++) fin = fin && isfinite(u[j].x) && isfinite(u[j].y);
+                for (int s = 0; s < S; s++) fin = fin && isfinite(u[s].x) && isfinite(u[s].y);
                 if (!__all_sync(FULL, fin)) {
                     status = NMPC_NOT_FINITE;
                     phase = PH_EXIT;
                     continue;
                 }
                 W.ld(V_UHALF, u);
-                inner_status = cont ? NMPC_CONVERGED : NMPC_NOT_CONVERGED_ITERATIONS;
+                inner_status = timed_out ? NMPC_NOT_CONVERGED_OUT_OF_TIME : (cont ? NMPC_CONVERGED : NMPC_NOT_CONVERGED_ITERATIONS);
                 status = inner_status;
+                // F2(u) for the outer loop (group 0) and f(u) = psi with c = 0 (group 1), should this be the end
 #pragma unroll
-                for (int j = 0; j < P; j++) x[j] = u[j];
-                mode = MODE_F2;
+                for (int s = 0; s < S; s++) x[s] = u[s];
+                pn_eval = (grp == 1) ? make_pen(0.0) : pn;
                 phase = PH_F2;
                 break;
             }
-#if NMPC_HELP_R > 0
-            case PH_HELP_WAIT: {
-                // poll the job records of every warp of the CTA: lane l looks at record (r, o) = (l / nwarps, l % nwarps),
-                // so the lowest set bit of the vote is the most urgent trial (smallest r) on offer
-                const int njobs = nwarps * (NMPC_HELP_R + 1);
-                int j = -1;
-                const uint32_t a_part = a_live + 4u + 4u * ((threadIdx.x >> 5) & 3u);  // this warp's sub-partition
-                for (;;) {
-                    if (ldv_shared(a_live) <= 0) return 0;
-                    if (ldv_shared(a_part) > NMPC_HELP_PART_MAX) {  // owners share this sub-partition: stay out of their way
-                        __nanosleep(2000);
-                        continue;
-                    }
-                    unsigned m = 0;
-                    int base = 0;
-                    for (; base < njobs && !m; base += 32) {
-                        const int l = base + lane;
-                        bool posted = false;
-                        if (l < njobs) {
-                            const int o = l % nwarps, r = l / nwarps;
-                            posted = ldv_shared(W.sb0 + (uint32_t)o * W.arena_bytes + (W.a_job - W.sb) + JOB_BYTES * r) == JOB_POSTED;
-                        }
-                        m = __ballot_sync(FULL, posted);
-                    }
-                    if (m) {
-                        const int l = base - 32 + __ffs(m) - 1;
-                        const int o = l % nwarps, r = l / nwarps;
-                        int ok = 0;
-                        if (lane == 0)
-                            ok = cas_shared(W.sb0 + (uint32_t)o * W.arena_bytes + (W.a_job - W.sb) + JOB_BYTES * r, JOB_POSTED,
-                                            JOB_TAKEN) == JOB_POSTED;
-                        ok = __shfl_sync(FULL, ok, 0);
-                        if (ok) {
-                            j = l;
-                            break;
-                        }
-                        continue;
-                    }
-                    __nanosleep(NMPC_HELP_SLEEP);
-                }
-                __threadfence_block();
-                const int o = j % nwarps, r = j / nwarps;
-                W.retarget(o);
-                const uint32_t aj = W.a_job + JOB_BYTES * r;
-                const int trial = ldsi(aj + 4u);
-                set_gamma(lds1(aj + 16u));
-                pn = make_pen(lds1(aj + 24u));
-                ls_seq = r;
-                W.ld(V_YL, yl);
-                if (trial == 0) {  // psi(uhalf) for the owner's Lipschitz test
-                    W.ld(V_UHALF, x);
-                    mode = MODE_COST;
-                    phase = PH_HELP_EVAL;
-                    break;
-                }
-                tau = 1.0;
-                for (int k = 0; k < trial; k++) tau /= 2.0;
-                const double om = 1.0 - tau;
-                double2 uo[P], fpr[P], dir[P];
-                W.ld(V_U, uo);
-                W.ld(V_FPR, fpr);
-                W.ld(V_DIR, dir);
-#pragma unroll
-                for (int jj = 0; jj < P; jj++) {
-                    x[jj].x = fma(-tau, dir[jj].x, fma(-om, fpr[jj].x, uo[jj].x));
-                    x[jj].y = fma(-tau, dir[jj].y, fma(-om, fpr[jj].y, uo[jj].y));
-                }
-                mode = MODE_GRAD;
-                phase = PH_HELP_EVAL;
-                break;
-            }
-#endif
             case PH_EXIT: {
 #ifdef NMPC_PROFILE
                 prof[6] = clock64() - tstart;
@@ -1530,241 +1279,156 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 return status;
             }
             default:
-                break;  // phases entered with (x, mode) already set
+                break;
         }
 
         // ------------------------------------------------------------------ the one evaluation site
         PH_ACCOUNT(-1);
-        pn_eval = (phase == PH_FINAL) ? make_pen(0.0) : pn;
 #ifdef NMPC_PROFILE
         const long long tp0 = clock64();
 #endif
-        const double psi = W.eval(mode, x, pn_eval, yl, g, pen, nullptr);
+        const double psi = W.eval(x, pn_eval, g, pen, nullptr);
 #ifdef NMPC_PROFILE
-        {
-            const long long dt = clock64() - tp0;
-            if (mode == MODE_GRAD) { prof[0] += dt; prof[1]++; } else { prof[2] += dt; prof[3]++; }
-        }
+        prof[0] += clock64() - tp0;
+        prof[1]++;
 #endif
-        if (mode == MODE_GRAD) n_grad++;
-        if (mode == MODE_COST && phase != PH_FINAL) n_cost++;
         PH_ACCOUNT(32 + phase);
+        __syncwarp();
 
         // ------------------------------------------------------------------ post
         switch (phase) {
-            case PH_INIT_A: {  // cost/gradient at u; then perturb u by h (estimate_loc_lip leaves it perturbed)
-                cost = psi;
-                W.st(V_GRAD, g);
-                double e[P];
-#pragma unroll
-                for (int j = 0; j < P; j++) {
-                    const double ex_ = EPSILON_LIPSCHITZ * u[j].x, ey_ = EPSILON_LIPSCHITZ * u[j].y;
-                    double hx = W.act[j] ? ((ex_ > DELTA_LIPSCHITZ) ? ex_ : DELTA_LIPSCHITZ) : 0.0;
-                    double hy = W.act[j] ? ((ey_ > DELTA_LIPSCHITZ) ? ey_ : DELTA_LIPSCHITZ) : 0.0;
-                    e[j] = fma(hy, hy, hx * hx);
-                    u[j].x = u[j].x + hx;
-                    u[j].y = u[j].y + hy;
-                    x[j] = u[j];
-                }
-                sput(H_NORMH, sqrt(hsum<P>(e)));
-                mode = MODE_GRAD;
-                phase = PH_INIT_B;
-                break;
-            }
-            case PH_INIT_B: {
-                double2 gr[P], gs[P], uh[P];
+            case PH_INIT: {  // group 0: cost / gradient at u; group 1: gradient at u + h -> local Lipschitz estimate
+                cost = __shfl_sync(FULL, psi, 0);
+                W.st(V_GRAD, g, 0);
+                W.st(V_T0, g, 1);
+                __syncwarp();
+                double2 gr[S], gh[S], gs[S], uh[S];
                 W.ld(V_GRAD, gr);
-                const double lip = sqrt(wdiff2<P>(g, gr)) / sget(H_NORMH);
+                W.ld(V_T0, gh);
+                const double lip = sqrt(gsum<G>(diff2(gh, gr))) / sget(H_NORMH);
                 sput(H_LIP, lip);
                 set_gamma(GAMMA_L_COEFF / fmax(lip, MIN_L_ESTIMATE));
                 grad_step_half(u, gr, gs, uh);
+                W.st(V_GSTEP, gs);
+                W.st(V_UHALF, uh);
+                __syncwarp();
+                n_grad += 2;
                 num_iter = 0;
                 cont = true;
+                timed_out = false;
                 phase = PH_STEP_BEGIN;
                 break;
             }
-            case PH_LIP: {  // psi(uhalf); OpEn then re-evaluates psi(u): needed only when u was perturbed (iteration 0)
-                cost_half = psi;
-                if (iteration == 0) {
-#pragma unroll
-                    for (int j = 0; j < P; j++) x[j] = u[j];
-                    mode = MODE_COST;
-                    phase = PH_COST_U;
-                } else {
-                    n_cost++;  // the re-evaluation OpEn performs; its value is bit-identical to the cached cost
-                    phase = PH_LIP_LOOP;
-                }
-                break;
-            }
-            case PH_COST_U: {
-                cost = psi;
-                phase = PH_LIP_LOOP;
-                break;
-            }
-            case PH_LIP_RETRY: {
-                cost_half = psi;
-                double2 uh[P], fpr[P];
-                W.ld(V_UHALF, uh);
-                compute_fpr(uh, fpr);
-                W.st(V_FPR, fpr);
-                it_lip++;
-                phase = PH_LIP_LOOP;
-                break;
-            }
-            case PH_IT0: {
-                cost = psi;
-                W.st(V_GRAD, g);
-                double2 gs[P], uh[P];
-                grad_step_half(u, g, gs, uh);
-                iteration++;
-                phase = PH_STEP_DONE;
-                break;
-            }
-            case PH_LS: {
-                cost = psi;
-                double2 gs[P], uh[P];
-                grad_step_half(x, g, gs, uh);
-                double d2, gg;
-                {
-                    double e[P], f[P];
-#pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        double d0 = gs[j].x - uh[j].x, d1 = gs[j].y - uh[j].y;
-                        e[j] = fma(d1, d1, d0 * d0);
-                        f[j] = fma(g[j].y, g[j].y, g[j].x * g[j].x);
-                    }
-                    hsum2<P>(e, f, d2, gg);
-                }
-                double lhs = cost - (0.5 * gamma) * gg + (0.5 * d2) * inv_gamma;
-                bool evaluate = false;
-                while (lhs > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS) {
-                    tau /= 2.0;
-                    nls++;
-                    const double om = 1.0 - tau;
-                    double2 fpr[P], dir[P];
-                    W.ld(V_FPR, fpr);
-                    W.ld(V_DIR, dir);
-#pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        x[j].x = fma(-tau, dir[j].x, fma(-om, fpr[j].x, u[j].x));
-                        x[j].y = fma(-tau, dir[j].y, fma(-om, fpr[j].y, u[j].y));
-                    }
-#if NMPC_HELP_R > 0
-                    // was this trial offered to a helper?  DONE: take its result; TAKEN: wait for it;
-                    // POSTED: nobody picked it up -> withdraw it and evaluate here.
-                    const int r = (nls - 1) % NMPC_HELP_R;
-                    const uint32_t aj = W.a_job + JOB_BYTES * r;
-                    int got = 0;
-                    if (lane == 0) {
-                        int stt = ldv_shared(aj);
-                        if (stt != JOB_EMPTY && ldsi(aj + 4u) == nls && ldsi(aj + 8u) == ls_seq) {
-                            if (stt == JOB_POSTED && cas_shared(aj, JOB_POSTED, JOB_EMPTY) == JOB_POSTED) stt = JOB_EMPTY;
-                            if (stt != JOB_EMPTY) {
-                                while (ldv_shared(aj) != JOB_DONE) __nanosleep(20);
-                                got = 1;
-                            }
-                        }
-                    }
-                    got = __shfl_sync(FULL, got, 0);
-                    if (got) {
-                        __threadfence_block();
-                        cost = lds1(aj + 32u);
-                        lhs = lds1(aj + 40u);
-                        W.ld(V_JG + r, g);
-                        n_grad++;
-                        __syncwarp();
-                        // the record is free again: offer the trial NMPC_HELP_R steps ahead
-                        if (lane == 0) {
-                            if (nls + NMPC_HELP_R <= MAX_LINESEARCH_ITERATIONS && lhs > rhs_ls &&
-                                nls + NMPC_HELP_R <= ls_hint + NMPC_HELP_EXTRA + 1) {
-                                stsi(aj + 4u, nls + NMPC_HELP_R);
-                                __threadfence_block();
-                                stv_shared(aj, JOB_POSTED);
-                            } else {
-                                stv_shared(aj, JOB_EMPTY);
-                            }
-                        }
-                        if (!(lhs > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) grad_step_half(x, g, gs, uh);  // accepted
-                        continue;
-                    }
-#endif
-                    evaluate = true;
+            case PH_A: {  // first call of an iteration: group 0 holds psi(u_half), the other groups trials (or psi(u))
+                const double cost_half = __shfl_sync(FULL, psi, 0);
+                if (iteration == 0) cost = __shfl_sync(FULL, psi, G);
+                n_cost += 2;  // psi(u_half) and OpEn's re-evaluation of psi(u) (bit-identical to the cached cost)
+                if (lip_test_fails(cost_half)) {
+                    lip_halve();
                     break;
                 }
-                if (evaluate) {
-                    mode = MODE_GRAD;
-                    phase = PH_LS;
+                if (iteration == 0) {
+                    first_iteration_update(cost_half);
+                    break;
+                }
+                if (fbe_valid) {
+                    // the envelope at u is the accepted trial's left-hand side of the previous line search
+                    // (same cost, gradient, gamma and stored gstep/uhalf: bit-identical), unless gamma changed
+                    rhs_ls = fbe_u - sigma * (norm_fpr * norm_fpr);
                 } else {
-#if NMPC_HELP_R > 0
-                    if (lane < NMPC_HELP_R) {  // withdraw what is still on offer
-                        const uint32_t aj = W.a_job + JOB_BYTES * lane;
-                        if (ldv_shared(aj) == JOB_POSTED) cas_shared(aj, JOB_POSTED, JOB_EMPTY);
-                    }
-#endif
-                    W.st(V_GRAD, g);
-#pragma unroll
-                    for (int j = 0; j < P; j++) u[j] = x[j];
-                    ls_hint = nls;
-                    fbe_u = lhs;
+                    rhs_from_envelope();
+                }
+            }  // fall through: check the trials this call evaluated
+            case PH_LS: {
+                double2 gs[S], uh[S];
+                grad_step_half(x, g, gs, uh);
+                double d2 = diff2(gs, uh), gg = dot(g, g);
+                gsum2<G>(d2, gg);
+                const double lhs = psi - (0.5 * gamma) * gg + (0.5 * d2) * inv_gamma;
+                int e = e0 + grp - gfirst;  // this group's trial
+                // linesearch(): the first trial with lhs <= rhs is kept; the trial after MAX halvings is kept anyway
+                const bool ok = grp >= gfirst && (!(lhs > rhs_ls) || e >= MAX_LINESEARCH_ITERATIONS);
+                const unsigned m = __ballot_sync(FULL, ok);
+                if (m) {
+                    const int src = __ffs(m) - 1;  // first lane of the accepting group
+                    const int k = src / G;
+                    e = e0 + k - gfirst;
+                    n_grad += (e > MAX_LINESEARCH_ITERATIONS ? MAX_LINESEARCH_ITERATIONS : e) + 1;
+                    __syncwarp();
+                    W.st(V_U, x, k);
+                    W.st(V_GRAD, g, k);
+                    W.st(V_GSTEP, gs, k);
+                    W.st(V_UHALF, uh, k);
+                    cost = __shfl_sync(FULL, psi, src);
+                    fbe_u = __shfl_sync(FULL, lhs, src);
                     fbe_valid = true;
+                    __syncwarp();
+                    W.ld(V_U, u);
                     iteration++;
                     phase = PH_STEP_DONE;
+                } else {
+                    e0 += NG - gfirst;
+                    gfirst = 0;
+                    form_trials(uh);
+                    phase = PH_LS;
                 }
                 break;
             }
-#if NMPC_HELP_R > 0
-            case PH_HELP_EVAL: {  // helper: envelope value of the trial, results into the owner's arena
-                if (mode == MODE_COST) {
-                    const uint32_t ajc = W.a_job + JOB_BYTES * ls_seq;
-                    if (lane == 0) sts1(ajc + 32u, psi);
-                    __threadfence_block();
-                    __syncwarp();
-                    if (lane == 0) stv_shared(ajc, JOB_DONE);
-                    phase = PH_HELP_WAIT;
+            case PH_RETRY: {  // psi(u_half) after a halving of gamma (every group evaluated the same point)
+                const double cost_half = psi;
+                n_cost++;
+                double2 uh[S], fpr[S], gr[S];
+                W.ld(V_UHALF, uh);
+                W.ld(V_GRAD, gr);
+                compute_fpr(uh, fpr);
+                __syncwarp();
+                W.st(V_FPR, fpr);
+                ip = gsum<G>(dot(gr, fpr));
+                it_lip++;
+                if (lip_test_fails(cost_half)) {
+                    lip_halve();
                     break;
                 }
-                double e[P], f[P], d2, gg;
-#pragma unroll
-                for (int j = 0; j < P; j++) {
-                    const double gsx = fma(-gamma, g[j].x, x[j].x), gsy = fma(-gamma, g[j].y, x[j].y);
-                    const double uhx = W.act[j] ? clampd(gsx, cfg.lin_vel_min, cfg.lin_vel_max) : 0.0;
-                    const double uhy = W.act[j] ? clampd(gsy, -cfg.ang_vel_max, cfg.ang_vel_max) : 0.0;
-                    const double d0 = gsx - uhx, d1 = gsy - uhy;
-                    e[j] = fma(d1, d1, d0 * d0);
-                    f[j] = fma(g[j].y, g[j].y, g[j].x * g[j].x);
+                // lbfgs update_hessian on the emptied buffer: remember (u, fpr)
+                lb_first = 0;
+                W.st(V_OLDS, u);
+                W.st(V_OLDG, fpr);
+                if (iteration == 0) {
+                    first_iteration_update(cost_half);
+                    break;
                 }
-                hsum2<P>(e, f, d2, gg);
-                const double lhs = psi - (0.5 * gamma) * gg + (0.5 * d2) * inv_gamma;
-                const uint32_t aj = W.a_job + JOB_BYTES * ls_seq;
-                W.st(V_JG + ls_seq, g);
-                if (lane == 0) {
-                    sts1(aj + 32u, psi);
-                    sts1(aj + 40u, lhs);
-                }
-                __threadfence_block();
+                W.st(V_DIR, fpr);  // empty memory: direction = fpr
                 __syncwarp();
-                if (lane == 0) stv_shared(aj, JOB_DONE);
-                phase = PH_HELP_WAIT;
+                rhs_from_envelope();
+                e0 = 0;
+                gfirst = 0;
+                form_trials(uh);
+                phase = PH_LS;
                 break;
             }
-#endif
             case PH_F2: {  // multipliers y+ = y + c*(F1 - Proj_C(F1 + y/c)); infeasibilities; outer-loop logic
-                double2 yp[P];
-                double e[P];
+                const double f_cost = __shfl_sync(FULL, psi, G);  // group 1 evaluated with c = 0
+                double2 yl[S], yp[S];
+                W.ld(V_YL, yl);
+                double e = 0.0;
+                {
+                    double vp0, wp0;
+                    W.prev_controls(u, vp0, wp0);
 #pragma unroll
-                for (int j = 0; j < P; j++) {
-                    double vp, wp_;
-                    W.prev_controls(u, j, vp, wp_);
-                    const double wa = (u[j].x - vp) * inv_ts, ww = (u[j].y - wp_) * inv_ts;
-                    double za = wa + yl[j].x / pn.c, zw = ww + yl[j].y / pn.c;
-                    za = clampd(za, cfg.lin_acc_min, cfg.lin_acc_max);
-                    zw = clampd(zw, -cfg.ang_acc_max, cfg.ang_acc_max);
-                    yp[j].x = W.act[j] ? fma(pn.c, wa - za, yl[j].x) : 0.0;
-                    yp[j].y = W.act[j] ? fma(pn.c, ww - zw, yl[j].y) : 0.0;
-                    double d0 = yp[j].x - yl[j].x, d1 = yp[j].y - yl[j].y;
-                    e[j] = W.act[j] ? fma(d1, d1, d0 * d0) : 0.0;
+                    for (int s = 0; s < S; s++) {
+                        const double vp = (s == 0) ? vp0 : u[s > 0 ? s - 1 : 0].x, wp_ = (s == 0) ? wp0 : u[s > 0 ? s - 1 : 0].y;
+                        const double wa = (u[s].x - vp) * inv_ts, ww = (u[s].y - wp_) * inv_ts;
+                        double za = wa + yl[s].x / pn.c, zw = ww + yl[s].y / pn.c;
+                        za = clampd(za, cfg.lin_acc_min, cfg.lin_acc_max);
+                        zw = clampd(zw, -cfg.ang_acc_max, cfg.ang_acc_max);
+                        yp[s].x = W.act[s] ? fma(pn.c, wa - za, yl[s].x) : 0.0;
+                        yp[s].y = W.act[s] ? fma(pn.c, ww - zw, yl[s].y) : 0.0;
+                        const double d0 = yp[s].x - yl[s].x, d1 = yp[s].y - yl[s].y;
+                        const double t = W.act[s] ? fma(d1, d1, d0 * d0) : 0.0;
+                        e = (s == 0) ? t : e + t;
+                    }
                 }
-                const double dynp = sqrt(hsum<P>(e)), f2np = sqrt(pen);
+                const double dynp = sqrt(gsum<G>(e)), f2np = sqrt(__shfl_sync(FULL, pen, 0));
                 const double akkt_tol = sget(H_AKKT);
                 sput(H_DYNP, dynp);
                 sput(H_F2NP, f2np);
@@ -1785,8 +1449,9 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                     alm_iter++;
                     sput(H_DYN, dynp);
                     sput(H_F2N, f2np);
-#pragma unroll
-                    for (int j = 0; j < P; j++) yl[j] = yp[j];
+                    __syncwarp();
+                    W.st(V_YL, yp);
+                    __syncwarp();
                     if (num_outer >= cfg.max_outer_iterations) {
                         status = NMPC_NOT_CONVERGED_ITERATIONS;
                         finished = true;
@@ -1794,19 +1459,12 @@ __device__ int solve_problem(Warp<P, NF>& W, double2 (&u)[P], double2 (&yl)[P], 
                 } else if (num_outer == cfg.max_outer_iterations) {
                     status = NMPC_NOT_CONVERGED_ITERATIONS;
                 }
+                st_out.cost = f_cost;
                 if (finished) {
-#pragma unroll
-                    for (int j = 0; j < P; j++) x[j] = u[j];
-                    mode = MODE_COST;
-                    phase = PH_FINAL;
+                    phase = PH_EXIT;
                 } else {
                     phase = PH_OUTER_BEGIN;
                 }
-                break;
-            }
-            case PH_FINAL: {
-                st_out.cost = psi;
-                phase = PH_EXIT;
                 break;
             }
             default:

@@ -15,84 +15,76 @@
 #include "nmpc_device.cuh"
 #include "nmpc_fleet.cuh"
 
+// Warps (problems in flight) per SM.  One CTA per SM; the cap is what the register file allows for each
+// instantiation (32 * cap threads per CTA bound the registers per thread through __launch_bounds__).
 #ifndef NMPC_WARPS
-#define NMPC_WARPS 12  // warps (problems in flight) per SM; 32*NMPC_WARPS threads per CTA bounds the registers
+#define NMPC_WARPS 8  // two warps per SM sub-partition: 255 registers per thread; three (12 warps, 168 registers) spill and lose 30 %
 #endif
-// Longer horizons keep 2-3 steps per lane in registers and their arenas are larger (27 KB at N=40, 61 KB at
-// N=80/Nobs=200), so fewer warps fit anyway: cap the CTA accordingly and let ptxas use the registers.
-__host__ __device__ constexpr int warps_cap(int P) { return P == 1 ? NMPC_WARPS : (P == 2 ? 8 : 5); }
+__host__ __device__ constexpr int warps_cap(int G, int S) {
+    return (G == 8 || S <= 2) ? NMPC_WARPS : (S == 3 ? 8 : (S == 4 ? 6 : 4));
+}
 
-template <int P, int NF, bool HC>
-__global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const __grid_constant__ KArgs a) {
+// load (u0, y0) of problem b: u into registers (every group holds the vector), y into the arena
+template <int G, int S>
+__device__ __forceinline__ void load_start(const KArgs& a, Warp<G, S>& W, int b, double2 (&u)[S]) {
+    const int N = W.N;
+    const double* U0 = a.U + (size_t)b * 2 * N;
+    const double* Y0 = a.Y ? a.Y + (size_t)b * 2 * N : nullptr;
+    double2 yl[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const int t = W.tix[s];
+        u[s] = (t < N) ? *reinterpret_cast<const double2*>(U0 + 2 * t) : make_double2(0.0, 0.0);
+        yl[s] = (t < N && Y0) ? make_double2(Y0[t], Y0[N + t]) : make_double2(0.0, 0.0);
+    }
+    W.st(V_YL, yl);
+    __syncwarp();
+}
+
+template <int G, int S>
+__global__ void __launch_bounds__(32 * warps_cap(G, S), 1) nmpc_solve_kernel(const __grid_constant__ KArgs a) {
     const nmpc_config& cfg = a.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const Lay L = make_layout(cfg.N_hor, cfg.Nobs, cfg.Ndynobs);
-    const int N = NF ? NF : cfg.N_hor;
-    Warp<P, NF> W(cfg, L, warp, lane);
-    // warps of this CTA that still own (or may still fetch) a problem; the others serve as helpers
-    // [0] all, [1 + s] those on SM sub-partition s = warp % 4
-    __shared__ int cta_live[5];
-    const uint32_t a_live = (uint32_t)__cvta_generic_to_shared(&cta_live[0]);
-    if (threadIdx.x < 5) cta_live[threadIdx.x] = (threadIdx.x == 0) ? nwarps : (nwarps - (int)threadIdx.x + 1 + 3) / 4;
-    if (lane < NMPC_HELP_R + 1) stsi(W.a_job + JOB_BYTES * lane, JOB_EMPTY);
-    __syncthreads();
+    const int N = cfg.N_hor;
+    Warp<G, S> W(cfg, L, warp, lane);
     // First wave: warp w of CTA c takes problem c + gridDim.x * w, so a batch smaller than the machine is spread
-    // over the SMs (one or two owners per SM, the other warps help) instead of filling a few CTAs; afterwards the
-    // problems come from the atomic queue.
-    bool helper = false, first = true;
+    // over the SMs instead of filling a few CTAs; afterwards the problems come from the atomic queue.
+    bool first = true;
     for (;;) {
         int b = 0;
-        if (!helper) {
-            if (first) {
-                b = (int)(blockIdx.x + gridDim.x * warp);
-                first = false;
-            } else {
-                if (lane == 0) b = (int)(gridDim.x * nwarps + atomicAdd(a.counter, 1u));
-                b = __shfl_sync(FULL, b, 0);
-            }
-            if (b < a.B && a.order) b = a.order[b];
-            if (b >= a.B) {  // queue empty: this warp will not own a problem again
-                if (lane == 0) {
-                    add_shared(a_live + 4u + 4u * (warp & 3), -1);
-                    add_shared(a_live, -1);
-                }
-                if (NMPC_HELP_R == 0 || nwarps == 1) break;
-                helper = true;
-            } else if (a.skip && a.skip[b]) {
-                continue;
-            }
-        }
-        double2 u[P], yl[P];
-        if (!helper) {
-            W.stage(a.P + (size_t)b * a.np);
-            const double* U0 = a.U + (size_t)b * 2 * N;
-            const double* Y0 = a.Y ? a.Y + (size_t)b * 2 * N : nullptr;
-#pragma unroll
-            for (int j = 0; j < P; j++) {
-                const int t = lane + 32 * j;
-                u[j] = (t < N) ? *reinterpret_cast<const double2*>(U0 + 2 * t) : make_double2(0.0, 0.0);
-                yl[j] = (t < N && Y0) ? make_double2(Y0[t], Y0[N + t]) : make_double2(0.0, 0.0);
-            }
+        if (first) {
+            b = (int)(blockIdx.x + gridDim.x * warp);
+            first = false;
         } else {
-#pragma unroll
-            for (int j = 0; j < P; j++) u[j] = yl[j] = make_double2(0.0, 0.0);
+            if (lane == 0) b = (int)(gridDim.x * nwarps + atomicAdd(a.counter, 1u));
+            b = __shfl_sync(FULL, b, 0);
         }
+        if (b < a.B && a.order) b = a.order[b];
+        if (b >= a.B) break;  // queue empty
+        if (a.skip && a.skip[b]) continue;
+        W.stage(a.P + (size_t)b * a.np);
+        double2 u[S];
+        load_start<G, S>(a, W, b, u);
         nmpc_stats st;
         st.cost = 0.0;
 #ifdef NMPC_PROFILE
-        const int status = solve_problem<P, NF, HC>(W, u, yl, st, helper, a_live, nwarps, a.dbg && !helper ? a.dbg + (size_t)b * 48 : nullptr);
+        const int status = solve_problem<G, S>(W, u, st, a.dbg ? a.dbg + (size_t)b * 48 : nullptr);
 #else
-        const int status = solve_problem<P, NF, HC>(W, u, yl, st, helper, a_live, nwarps);
+        const int status = solve_problem<G, S>(W, u, st);
 #endif
-        if (helper) break;  // no warp of the CTA owns a problem any more
+        if (W.grp == 0) {
+            double2 yl[S];
+            W.ld(V_YL, yl);
 #pragma unroll
-        for (int j = 0; j < P; j++) {
-            const int t = lane + 32 * j;
-            if (t < N) {
-                *reinterpret_cast<double2*>(a.U + (size_t)b * 2 * N + 2 * t) = u[j];
-                if (a.Y) {
-                    a.Y[(size_t)b * 2 * N + t] = yl[j].x;
-                    a.Y[(size_t)b * 2 * N + N + t] = yl[j].y;
+            for (int s = 0; s < S; s++) {
+                const int t = W.tix[s];
+                if (t < N) {
+                    *reinterpret_cast<double2*>(a.U + (size_t)b * 2 * N + 2 * t) = u[s];
+                    if (a.Y) {
+                        a.Y[(size_t)b * 2 * N + t] = yl[s].x;
+                        a.Y[(size_t)b * 2 * N + N + t] = yl[s].y;
+                    }
                 }
             }
         }
@@ -103,39 +95,31 @@ __global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_solve_kernel(const 
     }
 }
 
-// Probe for the longest-first schedule: |grad psi(u0)|^2 of every problem — ONE evaluation, 1/3700 of an average
-// solve — ranks the problems by the work they will need (Spearman 0.82 with the inner-iteration count on the
-// BASELINE config-2 batch; tools/ and DESIGN.md §5).  The kernel writes a sort bucket per problem (exponent and three
+// Probe for the longest-first schedule: |grad psi(u0)|^2 of every problem — ONE evaluation, a few thousandths of an
+// average solve — ranks the problems by the work they will need (Spearman 0.82 with the inner-iteration count on the
+// BASELINE config-2 batch).  The kernel writes a sort bucket per problem (exponent and three
 // mantissa bits of the squared norm, descending) and the bucket histogram; two tiny kernels turn that into the order
 // in which the solve kernel hands the problems out.  Scheduling only: results do not depend on it.
-template <int P, int NF>
-__global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_probe_kernel(const __grid_constant__ KArgs a) {
+template <int G, int S>
+__global__ void __launch_bounds__(32 * warps_cap(G, S), 1) nmpc_probe_kernel(const __grid_constant__ KArgs a) {
     const nmpc_config& cfg = a.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Lay L = make_layout(cfg.N_hor, cfg.Nobs, cfg.Ndynobs);
-    const int N = NF ? NF : cfg.N_hor;
     const int wpb = blockDim.x >> 5;
-    Warp<P, NF> W(cfg, L, warp, lane);
+    Warp<G, S> W(cfg, L, warp, lane);
     const Pen pn = make_pen(cfg.initial_penalty);
     for (int b = blockIdx.x * wpb + warp; b < a.B; b += gridDim.x * wpb) {
         int bucket = PROBE_BUCKETS - 1;  // skipped rows go last
         if (!(a.skip && a.skip[b])) {
             W.stage(a.P + (size_t)b * a.np);
-            double2 u[P], yl[P], g[P];
-            const double* U0 = a.U + (size_t)b * 2 * N;
-            const double* Y0 = a.Y ? a.Y + (size_t)b * 2 * N : nullptr;
-#pragma unroll
-            for (int j = 0; j < P; j++) {
-                const int t = lane + 32 * j;
-                u[j] = (t < N) ? *reinterpret_cast<const double2*>(U0 + 2 * t) : make_double2(0.0, 0.0);
-                yl[j] = (t < N && Y0) ? make_double2(Y0[t], Y0[N + t]) : make_double2(0.0, 0.0);
-            }
+            double2 u[S], g[S];
+            load_start<G, S>(a, W, b, u);
             double pen;
-            W.eval(MODE_GRAD, u, pn, yl, g, pen, nullptr);
-            double e[P];
+            W.eval(u, pn, g, pen, nullptr);
+            double e = fma(g[0].y, g[0].y, g[0].x * g[0].x);
 #pragma unroll
-            for (int j = 0; j < P; j++) e[j] = fma(g[j].y, g[j].y, g[j].x * g[j].x);
-            const double k = hsum<P>(e);
+            for (int s = 1; s < S; s++) e = e + fma(g[s].y, g[s].y, g[s].x * g[s].x);
+            const double k = gsum<G>(e);
             // exponent + 3 mantissa bits, window 2^-64 .. 2^64; NaN / inf count as hardest
             const int hi = (int)((unsigned long long)__double_as_longlong(k) >> 49) & 0x7fff;
             int idx = hi - ((1023 - 64) << 3);
@@ -169,69 +153,79 @@ __global__ void __launch_bounds__(256) order_scatter_kernel(const int32_t* bucke
 }
 
 // parity hook: psi, grad, F1, F2 for B (p, u, c, y) tuples
-template <int P, int NF>
-__global__ void __launch_bounds__(32 * warps_cap(P), 1) nmpc_eval_kernel(const __grid_constant__ KArgs a) {
+template <int G, int S>
+__global__ void __launch_bounds__(32 * warps_cap(G, S), 1) nmpc_eval_kernel(const __grid_constant__ KArgs a) {
     const nmpc_config& cfg = a.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Lay L = make_layout(cfg.N_hor, cfg.Nobs, cfg.Ndynobs);
-    const int N = NF ? NF : cfg.N_hor, nf2 = cfg.Nobs + cfg.Ndynobs;
+    const int N = cfg.N_hor, nf2 = cfg.Nobs + cfg.Ndynobs;
     const int wpb = blockDim.x >> 5;
-    Warp<P, NF> W(cfg, L, warp, lane);
+    Warp<G, S> W(cfg, L, warp, lane);
     for (int b = blockIdx.x * wpb + warp; b < a.B; b += gridDim.x * wpb) {
         W.stage(a.P + (size_t)b * a.np);
-        double2 u[P], yl[P], g[P];
-        const double* U0 = a.U + (size_t)b * 2 * N;
-        const double* Y0 = a.Y ? a.Y + (size_t)b * 2 * N : nullptr;
-#pragma unroll
-        for (int j = 0; j < P; j++) {
-            const int t = lane + 32 * j;
-            u[j] = (t < N) ? make_double2(U0[2 * t], U0[2 * t + 1]) : make_double2(0.0, 0.0);
-            yl[j] = (t < N && Y0) ? make_double2(Y0[t], Y0[N + t]) : make_double2(0.0, 0.0);
-        }
+        double2 u[S], g[S];
+        load_start<G, S>(a, W, b, u);
         double* F2g = a.F2 ? a.F2 + (size_t)b * nf2 : nullptr;
         if (F2g)
-            for (int k = lane; k < nf2; k += 32) F2g[k] = 0.0;  // skipped (zero-radius) slots report exactly 0
+            for (int k = lane; k < nf2; k += 32) F2g[k] = 0.0;  // slots nobody is inside of report exactly 0
         __syncwarp();
         const Pen pn = make_pen(a.cvec[b]);
         double pen;
-        const double psi = W.eval(MODE_GRAD, u, pn, yl, g, pen, F2g);
+        const double psi = W.eval(u, pn, g, pen, F2g);
         if (lane == 0 && a.psi) a.psi[b] = psi;
         const double inv_ts = W.hdr(H_INVTS);
+        double vp0, wp0;
+        W.prev_controls(u, vp0, wp0);
+        if (W.grp == 0) {
 #pragma unroll
-        for (int j = 0; j < P; j++) {
-            const int t = lane + 32 * j;
-            double vp, wp_;
-            W.prev_controls(u, j, vp, wp_);
-            if (t < N) {
-                if (a.grad) {
-                    a.grad[(size_t)b * 2 * N + 2 * t] = g[j].x;
-                    a.grad[(size_t)b * 2 * N + 2 * t + 1] = g[j].y;
-                }
-                if (a.F1) {
-                    a.F1[(size_t)b * 2 * N + t] = (u[j].x - vp) * inv_ts;
-                    a.F1[(size_t)b * 2 * N + N + t] = (u[j].y - wp_) * inv_ts;
+            for (int s = 0; s < S; s++) {
+                const int t = W.tix[s];
+                const double vp = (s == 0) ? vp0 : u[s > 0 ? s - 1 : 0].x, wp_ = (s == 0) ? wp0 : u[s > 0 ? s - 1 : 0].y;
+                if (t < N) {
+                    if (a.grad) {
+                        a.grad[(size_t)b * 2 * N + 2 * t] = g[s].x;
+                        a.grad[(size_t)b * 2 * N + 2 * t + 1] = g[s].y;
+                    }
+                    if (a.F1) {
+                        a.F1[(size_t)b * 2 * N + t] = (u[s].x - vp) * inv_ts;
+                        a.F1[(size_t)b * 2 * N + N + t] = (u[s].y - wp_) * inv_ts;
+                    }
                 }
             }
         }
+        __syncwarp();
     }
 }
 
 // ---------------------------------------------------------------------------------
 // host side: the C ABI (include/nmpc_b200.h)
+// Work-queue state of one launch.  A handle keeps a small ring of these so that launches on different streams
+// (double buffering, or a device-pointer call followed by a host-buffer call) never share a queue counter or the
+// probe / order scratch: a context is reused only after the launch that last used it has finished (event wait on
+// the new launch's stream).
+#define NMPC_LAUNCH_CTXS 4
+struct launch_ctx {
+    unsigned int* counter;
+    int32_t *pbucket, *porder, *phist;  // longest-first schedule of large batches (probe + counting sort)
+    int pcap;
+    cudaEvent_t done;
+    bool used;
+};
 struct nmpc_handle {
     nmpc_config cfg;
-    int device, sm_count, np, P, warps_per_cta;
+    int device, sm_count, np, G, S, warps_per_cta;
     size_t smem_bytes;
     cudaStream_t stream;
-    unsigned int* counter;
+    launch_ctx ctx[NMPC_LAUNCH_CTXS];
+    int next_ctx;
     // scratch for the host-buffer entry points
     double *dP, *dU, *dY;
     int32_t* dstatus;
     nmpc_stats* dstats;
     int cap;
-    // longest-first schedule of large batches (probe + counting sort)
-    int32_t *pbucket, *porder, *phist;
-    int pcap;
+    // scratch of nmpc_eval_batch
+    double* ebuf;
+    size_t ebuf_len;
     // nmpc_call state (what OpEn's TCP server keeps between requests)
     double *call_u, *call_y;
     int64_t launches;
@@ -286,16 +280,6 @@ const char* nmpc_exit_status_name(int32_t s) {
 
 const char* nmpc_last_error(nmpc_handle* h) { return h ? h->err : "null handle"; }
 
-// Optional compile-time-N instantiation (fully unrolled cross-track loop with a tree arg-min).  Measured on
-// B200 (round 1, tools/variants.py): a lone warp's evaluation gets 15 % faster, but the larger hot loop costs
-// more in instruction fetch than it saves (config 2: 45.6k vs 48.6k solves/s), so it is off by default.
-// 0: never use the latency instantiation, 1: always, 2: for batches of at most two problems per SM
-#ifndef NMPC_LATENCY_MODE
-#define NMPC_LATENCY_MODE 2
-#endif
-#ifndef NMPC_AUTO_ORDER_ALL
-#define NMPC_AUTO_ORDER_ALL 0  // 1: also order batches that fit the warp slots (spreads the long solves over the SMs)
-#endif
 #ifndef NMPC_AUTO_ORDER
 #define NMPC_AUTO_ORDER 1  // batches larger than the warp slots: probe + longest-first order before the solve
 #endif
@@ -305,40 +289,14 @@ const char* nmpc_last_error(nmpc_handle* h) { return h ? h->err : "null handle";
 #ifndef NMPC_ZEROCOPY
 #define NMPC_ZEROCOPY 1  // nmpc_solve_batch on page-locked host buffers: no staging copies
 #endif
-#ifndef NMPC_FIXED_N
-#define NMPC_FIXED_N 0
-#endif
-// latency = true: the instantiation that also overlaps psi(uhalf) with the two-loop recursion (solve_problem<HC>)
-static const void* solve_kernel_for(int N, bool latency) {
-#if NMPC_FIXED_N > 0
-    if (N == NMPC_FIXED_N)
-        return latency ? (const void*)nmpc_solve_kernel<(NMPC_FIXED_N + 31) / 32, NMPC_FIXED_N, true>
-                       : (const void*)nmpc_solve_kernel<(NMPC_FIXED_N + 31) / 32, NMPC_FIXED_N, false>;
-#endif
-    const bool lat = latency && NMPC_HELP_R > 0 && NMPC_HELP_COST;
-    switch ((N + 31) / 32) {
-        case 1: return lat ? (const void*)nmpc_solve_kernel<1, 0, true> : (const void*)nmpc_solve_kernel<1, 0, false>;
-        case 2: return lat ? (const void*)nmpc_solve_kernel<2, 0, true> : (const void*)nmpc_solve_kernel<2, 0, false>;
-        default: return lat ? (const void*)nmpc_solve_kernel<3, 0, true> : (const void*)nmpc_solve_kernel<3, 0, false>;
-    }
-}
-static const void* probe_kernel_for(int N) {
-    switch ((N + 31) / 32) {
-        case 1: return (const void*)nmpc_probe_kernel<1, 0>;
-        case 2: return (const void*)nmpc_probe_kernel<2, 0>;
-        default: return (const void*)nmpc_probe_kernel<3, 0>;
-    }
-}
-static const void* eval_kernel_for(int N) {
-#if NMPC_FIXED_N > 0
-    if (N == NMPC_FIXED_N) return (const void*)nmpc_eval_kernel<(NMPC_FIXED_N + 31) / 32, NMPC_FIXED_N>;
-#endif
-    switch ((N + 31) / 32) {
-        case 1: return (const void*)nmpc_eval_kernel<1, 0>;
-        case 2: return (const void*)nmpc_eval_kernel<2, 0>;
-        default: return (const void*)nmpc_eval_kernel<3, 0>;
-    }
-}
+// one instantiation per horizon layout (nmpc_layout_for)
+#define NMPC_FOR_LAYOUT(KERNEL, G, S)                                   \
+    ((G) == 8 ? ((S) == 2 ? (const void*)KERNEL<8, 2> : (const void*)KERNEL<8, 3>)  \
+              : ((S) == 2 ? (const void*)KERNEL<16, 2>                               \
+                          : ((S) == 3 ? (const void*)KERNEL<16, 3> : ((S) == 4 ? (const void*)KERNEL<16, 4> : (const void*)KERNEL<16, 6>))))
+static const void* solve_kernel_for(const nmpc_handle* h) { return NMPC_FOR_LAYOUT(nmpc_solve_kernel, h->G, h->S); }
+static const void* probe_kernel_for(const nmpc_handle* h) { return NMPC_FOR_LAYOUT(nmpc_probe_kernel, h->G, h->S); }
+static const void* eval_kernel_for(const nmpc_handle* h) { return NMPC_FOR_LAYOUT(nmpc_eval_kernel, h->G, h->S); }
 
 int nmpc_create(const nmpc_config* cfg, int device, nmpc_handle** out) {
     if (!cfg || !out) return NMPC_ERR_INVALID;
@@ -353,7 +311,7 @@ int nmpc_create(const nmpc_config* cfg, int device, nmpc_handle** out) {
     h->cfg = *cfg;
     h->device = device;
     h->np = nmpc_param_len(cfg);
-    h->P = (cfg->N_hor + 31) / 32;
+    nmpc_layout_for(cfg->N_hor, h->G, h->S);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
         delete h;
@@ -375,18 +333,19 @@ int nmpc_create(const nmpc_config* cfg, int device, nmpc_handle** out) {
         delete h;
         return NMPC_ERR_INVALID;  // problem too large for one warp's arena
     }
-    if (w > warps_cap(h->P)) w = warps_cap(h->P);
+    if (w > warps_cap(h->G, h->S)) w = warps_cap(h->G, h->S);
     h->warps_per_cta = w;
     h->smem_bytes = per_warp * w;
-    e = cudaFuncSetAttribute(solve_kernel_for(h->cfg.N_hor, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    e = cudaFuncSetAttribute(solve_kernel_for(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(solve_kernel_for(h->cfg.N_hor, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+        e = cudaFuncSetAttribute(eval_kernel_for(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(eval_kernel_for(h->cfg.N_hor), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(probe_kernel_for(h->cfg.N_hor), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+        e = cudaFuncSetAttribute(probe_kernel_for(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&h->counter, sizeof(unsigned int));
+    for (int i = 0; i < NMPC_LAUNCH_CTXS && e == cudaSuccess; i++) {
+        e = cudaMalloc(&h->ctx[i].counter, sizeof(unsigned int));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ctx[i].done, cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&h->call_u, 2 * cfg->N_hor * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&h->call_y, 2 * cfg->N_hor * sizeof(double));
     if (e == cudaSuccess) e = cudaMemset(h->call_u, 0, 2 * cfg->N_hor * sizeof(double));
@@ -405,8 +364,13 @@ int nmpc_destroy(nmpc_handle* h) {
     if (!h) return NMPC_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->counter);
-    cudaFree(h->pbucket); cudaFree(h->porder); cudaFree(h->phist);
+    cudaDeviceSynchronize();  // launches on caller streams may still use the queue contexts
+    for (int i = 0; i < NMPC_LAUNCH_CTXS; i++) {
+        cudaFree(h->ctx[i].counter);
+        cudaFree(h->ctx[i].pbucket); cudaFree(h->ctx[i].porder); cudaFree(h->ctx[i].phist);
+        if (h->ctx[i].done) cudaEventDestroy(h->ctx[i].done);
+    }
+    cudaFree(h->ebuf);
     cudaFree(h->call_u);
     cudaFree(h->call_y);
     cudaFree(h->dP);
@@ -440,44 +404,49 @@ static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU,
     a.Y = dY;
     a.status = dstatus;
     a.stats = dstats;
-    a.counter = h->counter;
     a.skip = dskip;
     a.order = dorder;
-    if (NMPC_AUTO_ORDER && !dorder && B > (NMPC_AUTO_ORDER_ALL ? 2 * h->sm_count : h->sm_count * h->warps_per_cta)) {
+    // this launch's own queue state; if the context was used before, wait (on the device) for that launch
+    launch_ctx& c = h->ctx[h->next_ctx];
+    h->next_ctx = (h->next_ctx + 1) % NMPC_LAUNCH_CTXS;
+    if (c.used) CUDA_TRY(h, cudaStreamWaitEvent(s, c.done, 0));
+    c.used = true;
+    a.counter = c.counter;
+    if (NMPC_AUTO_ORDER && !dorder && B > h->sm_count * h->warps_per_cta) {
         // more problems than warp slots: rank them with one gradient evaluation each and start the long ones first
-        if (B > h->pcap) {
-            cudaFree(h->pbucket); cudaFree(h->porder); cudaFree(h->phist);
-            h->pbucket = h->porder = h->phist = nullptr; h->pcap = 0;
-            CUDA_TRY(h, cudaMalloc(&h->pbucket, (size_t)B * sizeof(int32_t)));
-            CUDA_TRY(h, cudaMalloc(&h->porder, (size_t)B * sizeof(int32_t)));
-            CUDA_TRY(h, cudaMalloc(&h->phist, PROBE_BUCKETS * sizeof(int32_t)));
-            h->pcap = B;
+        if (B > c.pcap) {
+            // the context's previous launch has at most been waited for on stream s, not on the host: drain it
+            // before its scratch is freed (only when a batch grows)
+            CUDA_TRY(h, cudaEventSynchronize(c.done));
+            cudaFree(c.pbucket); cudaFree(c.porder); cudaFree(c.phist);
+            c.pbucket = c.porder = c.phist = nullptr; c.pcap = 0;
+            CUDA_TRY(h, cudaMalloc(&c.pbucket, (size_t)B * sizeof(int32_t)));
+            CUDA_TRY(h, cudaMalloc(&c.porder, (size_t)B * sizeof(int32_t)));
+            CUDA_TRY(h, cudaMalloc(&c.phist, PROBE_BUCKETS * sizeof(int32_t)));
+            c.pcap = B;
         }
-        a.probe_bucket = h->pbucket;
-        a.probe_hist = h->phist;
-        CUDA_TRY(h, cudaMemsetAsync(h->phist, 0, PROBE_BUCKETS * sizeof(int32_t), s));
+        a.probe_bucket = c.pbucket;
+        a.probe_hist = c.phist;
+        CUDA_TRY(h, cudaMemsetAsync(c.phist, 0, PROBE_BUCKETS * sizeof(int32_t), s));
         int pgrid = (B + h->warps_per_cta - 1) / h->warps_per_cta;
         if (pgrid > h->sm_count) pgrid = h->sm_count;
         void* pargs[] = {&a};
-        CUDA_TRY(h, cudaLaunchKernel(probe_kernel_for(h->cfg.N_hor), dim3(pgrid), dim3(32 * h->warps_per_cta), pargs, h->smem_bytes, s));
-        order_scan_kernel<<<1, PROBE_BUCKETS, 0, s>>>(h->phist);
-        order_scatter_kernel<<<(B + 255) / 256, 256, 0, s>>>(h->pbucket, h->phist, h->porder, B);
+        CUDA_TRY(h, cudaLaunchKernel(probe_kernel_for(h), dim3(pgrid), dim3(32 * h->warps_per_cta), pargs, h->smem_bytes, s));
+        order_scan_kernel<<<1, PROBE_BUCKETS, 0, s>>>(c.phist);
+        order_scatter_kernel<<<(B + 255) / 256, 256, 0, s>>>(c.pbucket, c.phist, c.porder, B);
         h->launches += 3;
-        a.order = h->porder;
+        a.order = c.porder;
     }
 #ifdef NMPC_PROFILE
     a.dbg = g_dbg;
 #endif
-    CUDA_TRY(h, cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), s));
+    CUDA_TRY(h, cudaMemsetAsync(c.counter, 0, sizeof(unsigned int), s));
     int grid = h->sm_count;  // one persistent CTA per SM; fewer only if there are fewer problems than SMs
     if (grid > B) grid = B;
     if (grid < 1) grid = 1;
     void* args[] = {&a};
-    // batches of at most two problems per SM (SM sub-partitions stay free for helper warps from the start) run the
-    // latency instantiation; larger ones the plain one (measured crossover between B = 296 and 592 on 148 SMs)
-    const bool latency = (NMPC_LATENCY_MODE == 1) || (NMPC_LATENCY_MODE == 2 && B <= 2 * h->sm_count);  // 3: see HC_TAIL
-    CUDA_TRY(h, cudaLaunchKernel(solve_kernel_for(h->cfg.N_hor, latency), dim3(grid), dim3(32 * h->warps_per_cta), args,
-                                 h->smem_bytes, s));
+    CUDA_TRY(h, cudaLaunchKernel(solve_kernel_for(h), dim3(grid), dim3(32 * h->warps_per_cta), args, h->smem_bytes, s));
+    CUDA_TRY(h, cudaEventRecord(c.done, s));
     h->launches++;
     return NMPC_OK;
 }
@@ -529,9 +498,10 @@ int nmpc_solve_batch(nmpc_handle* h, int32_t B, const double* P, double* U, doub
         void* aY = Y ? pinned_alias(Y) : nullptr;
         void* aS = status ? pinned_alias(status) : nullptr;
         void* aT = stats ? pinned_alias(stats) : nullptr;
-        if (NMPC_ZEROCOPY && aP && aU && (!Y || aY) && (!status || aS) && (!stats || aT) && Y) {
+        if (NMPC_ZEROCOPY && aP && aU && (!Y || aY) && (!status || aS) && (!stats || aT)) {
             cudaStream_t s = h->stream;
             CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+            // Y == NULL: the kernel starts from zero multipliers and drops the multiplier state
             int rc0 = launch_solve(h, B, (const double*)aP, (double*)aU, (double*)aY, (int32_t*)aS, (nmpc_stats*)aT, s);
             if (rc0) return rc0;
             CUDA_TRY(h, cudaEventRecord(h->ev1, s));
@@ -607,45 +577,46 @@ int nmpc_eval_batch(nmpc_handle* h, int32_t B, const double* P, const double* U,
     if (!h || B < 0 || !P || !U || !c) return set_err(h, NMPC_ERR_INVALID, "nmpc_eval_batch: bad argument%s", "");
     if (B == 0) return NMPC_OK;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    const size_t n2 = 2 * (size_t)h->cfg.N_hor, nf2 = (size_t)h->cfg.Nobs + h->cfg.Ndynobs;
+    const size_t n2 = 2 * (size_t)h->cfg.N_hor, nf2 = (size_t)h->cfg.Nobs + h->cfg.Ndynobs, np = (size_t)h->np;
     cudaStream_t s = h->stream;
-    double *dP = 0, *dU = 0, *dY = 0, *dc = 0, *dpsi = 0, *dgrad = 0, *dF1 = 0, *dF2 = 0;
-    int rc = NMPC_OK;
-    cudaError_t e = cudaSuccess;
-#define TRY_(call) if (e == cudaSuccess) e = (call)
-    TRY_(cudaMalloc(&dP, (size_t)B * h->np * sizeof(double)));
-    TRY_(cudaMalloc(&dU, (size_t)B * n2 * sizeof(double)));
-    TRY_(cudaMalloc(&dY, (size_t)B * n2 * sizeof(double)));
-    TRY_(cudaMalloc(&dc, (size_t)B * sizeof(double)));
-    TRY_(cudaMalloc(&dpsi, (size_t)B * sizeof(double)));
-    TRY_(cudaMalloc(&dgrad, (size_t)B * n2 * sizeof(double)));
-    TRY_(cudaMalloc(&dF1, (size_t)B * n2 * sizeof(double)));
-    TRY_(cudaMalloc(&dF2, (size_t)(B * nf2 + 1) * sizeof(double)));
-    TRY_(cudaMemcpyAsync(dP, P, (size_t)B * h->np * sizeof(double), cudaMemcpyHostToDevice, s));
-    TRY_(cudaMemcpyAsync(dU, U, (size_t)B * n2 * sizeof(double), cudaMemcpyHostToDevice, s));
-    if (Y) TRY_(cudaMemcpyAsync(dY, Y, (size_t)B * n2 * sizeof(double), cudaMemcpyHostToDevice, s));
-    else TRY_(cudaMemsetAsync(dY, 0, (size_t)B * n2 * sizeof(double), s));
-    TRY_(cudaMemcpyAsync(dc, c, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, s));
-    if (e == cudaSuccess) {
-        KArgs a;
-        memset(&a, 0, sizeof(a));
-        a.cfg = h->cfg; a.B = B; a.np = h->np; a.P = dP; a.U = dU; a.Y = dY; a.cvec = dc;
-        a.psi = dpsi; a.grad = dgrad; a.F1 = dF1; a.F2 = dF2;
-        int grid = (B + h->warps_per_cta - 1) / h->warps_per_cta;
-        if (grid > 8 * h->sm_count) grid = 8 * h->sm_count;
-        void* args[] = {&a};
-        e = cudaLaunchKernel(eval_kernel_for(h->cfg.N_hor), dim3(grid), dim3(32 * h->warps_per_cta), args, h->smem_bytes, s);
-        h->launches++;
+    // one grow-only scratch block of the handle: P | U | Y | c | psi | grad | F1 | F2
+    const size_t need = (size_t)B * (np + 4 * n2 + 2 + nf2) + 1;
+    if (need > h->ebuf_len) {
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        cudaFree(h->ebuf);
+        h->ebuf = nullptr;
+        h->ebuf_len = 0;
+        CUDA_TRY(h, cudaMalloc(&h->ebuf, need * sizeof(double)));
+        h->ebuf_len = need;
     }
-    if (psi) TRY_(cudaMemcpyAsync(psi, dpsi, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (grad) TRY_(cudaMemcpyAsync(grad, dgrad, (size_t)B * n2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (F1) TRY_(cudaMemcpyAsync(F1, dF1, (size_t)B * n2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (F2 && nf2) TRY_(cudaMemcpyAsync(F2, dF2, (size_t)B * nf2 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    TRY_(cudaStreamSynchronize(s));
-#undef TRY_
-    if (e != cudaSuccess) rc = set_err(h, NMPC_ERR_CUDA, "nmpc_eval_batch: %s", cudaGetErrorString(e));
-    cudaFree(dP); cudaFree(dU); cudaFree(dY); cudaFree(dc); cudaFree(dpsi); cudaFree(dgrad); cudaFree(dF1); cudaFree(dF2);
-    return rc;
+    double* dP = h->ebuf;
+    double* dU = dP + (size_t)B * np;
+    double* dY = dU + (size_t)B * n2;
+    double* dc = dY + (size_t)B * n2;
+    double* dpsi = dc + B;
+    double* dgrad = dpsi + B;
+    double* dF1 = dgrad + (size_t)B * n2;
+    double* dF2 = dF1 + (size_t)B * n2;
+    CUDA_TRY(h, cudaMemcpyAsync(dP, P, (size_t)B * np * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(dU, U, (size_t)B * n2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (Y) CUDA_TRY(h, cudaMemcpyAsync(dY, Y, (size_t)B * n2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    else CUDA_TRY(h, cudaMemsetAsync(dY, 0, (size_t)B * n2 * sizeof(double), s));
+    CUDA_TRY(h, cudaMemcpyAsync(dc, c, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, s));
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.cfg = h->cfg; a.B = B; a.np = h->np; a.P = dP; a.U = dU; a.Y = dY; a.cvec = dc;
+    a.psi = dpsi; a.grad = dgrad; a.F1 = dF1; a.F2 = dF2;
+    int grid = (B + h->warps_per_cta - 1) / h->warps_per_cta;
+    if (grid > 8 * h->sm_count) grid = 8 * h->sm_count;
+    void* args[] = {&a};
+    CUDA_TRY(h, cudaLaunchKernel(eval_kernel_for(h), dim3(grid), dim3(32 * h->warps_per_cta), args, h->smem_bytes, s));
+    h->launches++;
+    if (psi) CUDA_TRY(h, cudaMemcpyAsync(psi, dpsi, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (grad) CUDA_TRY(h, cudaMemcpyAsync(grad, dgrad, (size_t)B * n2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (F1) CUDA_TRY(h, cudaMemcpyAsync(F1, dF1, (size_t)B * n2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (F2 && nf2) CUDA_TRY(h, cudaMemcpyAsync(F2, dF2, (size_t)B * nf2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return NMPC_OK;
 }
 
 
@@ -663,6 +634,11 @@ struct nmpc_fleet {
     bool have_order;
     bool loaded;  // plans complete (references uploaded or sampled)
     bool staged;  // nmpc_fleet_load has run
+    int64_t steps_done;  // receding-horizon steps enqueued since nmpc_fleet_load (bounds the schedule rows in use)
+    // grow-only scratch of nmpc_fleet_sample_refs
+    int32_t* dn_nodes;
+    double* dnodes;
+    size_t nodes_cap;
 };
 
 template <typename T>
@@ -737,6 +713,7 @@ int nmpc_fleet_destroy(nmpc_fleet* f) {
     cudaFree(a.log); cudaFree(a.n_logged);
     cudaFree(f->dU); cudaFree(f->dY); cudaFree(f->dstatus); cudaFree(f->dstats);
     cudaFree(f->dorder); cudaFree(f->dhist);
+    cudaFree(f->dn_nodes); cudaFree(f->dnodes);
     delete f;
     return NMPC_OK;
 }
@@ -787,6 +764,7 @@ int nmpc_fleet_load(nmpc_fleet* f, const int32_t* n_ref, const double* ref, cons
     f->loaded = have_ref;
     f->staged = true;
     f->have_order = false;
+    f->steps_done = 0;
     return NMPC_OK;
 }
 
@@ -802,11 +780,17 @@ int nmpc_fleet_sample_refs(nmpc_fleet* f, const int32_t* n_nodes, const double* 
         if (n_nodes[b] < 1 || n_nodes[b] > max_nodes) return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_sample_refs: n_nodes out of range%s", "");
     CUDA_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
-    int32_t* dn = nullptr;
-    double* dnodes = nullptr;
-    CUDA_TRY(h, cudaMalloc(&dn, B * sizeof(int32_t)));
-    cudaError_t e = cudaMalloc(&dnodes, B * max_nodes * 2 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dn, n_nodes, B * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    if (B * (size_t)max_nodes > f->nodes_cap) {
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        cudaFree(f->dn_nodes); cudaFree(f->dnodes);
+        f->dn_nodes = nullptr; f->dnodes = nullptr; f->nodes_cap = 0;
+        CUDA_TRY(h, cudaMalloc(&f->dn_nodes, B * sizeof(int32_t)));
+        CUDA_TRY(h, cudaMalloc(&f->dnodes, B * max_nodes * 2 * sizeof(double)));
+        f->nodes_cap = B * (size_t)max_nodes;
+    }
+    int32_t* dn = f->dn_nodes;
+    double* dnodes = f->dnodes;
+    cudaError_t e = cudaMemcpyAsync(dn, n_nodes, B * sizeof(int32_t), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dnodes, nodes, B * max_nodes * 2 * sizeof(double), cudaMemcpyHostToDevice, s);
     std::vector<int32_t> got(B);
     if (e == cudaSuccess) {
@@ -821,8 +805,6 @@ int nmpc_fleet_sample_refs(nmpc_fleet* f, const int32_t* n_nodes, const double* 
     if (e == cudaSuccess) e = cudaMemcpyAsync(got.data(), f->a.n_ref, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess && ref_out) e = cudaMemcpyAsync(ref_out, f->a.ref, B * fc.max_ref * 3 * sizeof(double), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(dn);
-    cudaFree(dnodes);
     if (e != cudaSuccess) return set_err(h, NMPC_ERR_CUDA, "nmpc_fleet_sample_refs: %s", cudaGetErrorString(e));
     for (size_t b = 0; b < B; b++)
         if (got[b] < 1 || got[b] > fc.max_ref) {
@@ -841,6 +823,11 @@ int nmpc_fleet_step(nmpc_fleet* f, int32_t n_steps) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const int B = f->fc.n_robots;
+    // step t reads schedule rows t .. t + N - 1 (src/path_generator.py:306-316): refuse to run past the end of
+    // the uploaded schedule instead of freezing the obstacles at their last pose
+    if (f->fc.n_sched > 0 && f->steps_done + n_steps + h->cfg.N_hor - 1 > f->fc.n_sched)
+        return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_step: the dynamic-obstacle schedule is too short for this many steps "
+                       "(n_sched rows must cover steps + N_hor - 1)%s", "");
     CUDA_TRY(h, cudaEventRecord(h->ev0, s));
     for (int k = 0; k < n_steps; k++) {
         fleet_assemble_kernel<<<(B * 32 + 255) / 256, 256, 0, s>>>(f->a);
@@ -848,7 +835,11 @@ int nmpc_fleet_step(nmpc_fleet* f, int32_t n_steps) {
         // fleets larger than the machine's warp slots: hand the robots out longest-first (by the previous step)
         const bool use_order = NMPC_FLEET_ORDER && f->have_order && B > h->sm_count * h->warps_per_cta;
         int rc = launch_solve(h, B, f->a.P, f->dU, f->dY, f->dstatus, f->dstats, s, f->a.done, use_order ? f->dorder : nullptr);
-        if (rc) return rc;
+        if (rc) {
+            cudaStreamSynchronize(s);  // what was enqueued so far finishes before the caller sees the error
+            return rc;
+        }
+        f->steps_done++;
         fleet_advance_kernel<<<(B + 255) / 256, 256, 0, s>>>(f->a);
         h->launches++;
         if (NMPC_FLEET_ORDER && B > h->sm_count * h->warps_per_cta) {

@@ -29,7 +29,7 @@ class NmpcConfig(C.Structure):
     _fields_ = [
         ("N_hor", C.c_int32), ("Nobs", C.c_int32), ("Ndynobs", C.c_int32),
         ("lbfgs_memory", C.c_int32), ("max_inner_iterations", C.c_int32),
-        ("max_outer_iterations", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("max_outer_iterations", C.c_int32), ("max_duration_micros", C.c_int32), ("reserved1", C.c_int32),
         ("ts", C.c_double),
         ("lin_vel_min", C.c_double), ("lin_vel_max", C.c_double), ("ang_vel_max", C.c_double),
         ("lin_acc_min", C.c_double), ("lin_acc_max", C.c_double), ("ang_acc_max", C.c_double),

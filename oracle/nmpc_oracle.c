@@ -24,16 +24,25 @@
  * against OpEn when it can be installed, not a cited fact.  Each function names
  * the OpEn routine it restates.
  *
- * ARITHMETIC CONTRACT (shared with the CUDA kernel).  IEEE binary64,
- * no implicit contraction (compile with -ffp-contract=off), explicit fma() exactly
- * where written, own sincos (Cody-Waite + fdlibm kernels, <= 2 ulp), reciprocals of
- * per-problem constants precomputed once, and reductions in the order a 32-lane
- * warp produces them: lane l owns time steps t = l + 32*j; full reductions are an
- * xor-butterfly over the 32 lane partials; prefix/suffix sums along the horizon
- * are Kogge-Stone scans with a carry between 32-step passes.  These orders differ
- * from a serial loop only in the last bits, and they let the GPU result be compared
- * BIT FOR BIT with this file.  An independent NumPy/torch restatement with libm,
- * divisions and serial sums (oracle/oracle_np.py) checks this file to 1e-11.
+ * TWO BUILDS OF THIS FILE (oracle/Makefile):
+ *
+ *  libnmpc_oracle.so  — the ARITHMETIC CONTRACT shared with the CUDA kernel:
+ *    IEEE binary64, no implicit contraction (-ffp-contract=off), explicit fma() exactly where
+ *    written, own sincos (Cody-Waite + fdlibm kernels, <= 2 ulp), reciprocals of per-problem
+ *    constants precomputed once, and every sum over the horizon in the order the kernel's
+ *    evaluation GROUP produces it: the horizon is cut into G chunks of S consecutive steps
+ *    (layout_for(): G = 8 lanes for N <= 24, else 16; lane i owns steps S*i .. S*i+S-1);
+ *    a sum is the serial sum of each chunk followed by an xor-butterfly over the G chunk
+ *    partials; prefix / suffix sums along the horizon are the serial scan of each chunk plus
+ *    a Kogge-Stone scan of the chunk totals.  These orders differ from a serial loop only in
+ *    the last bits, and they let the GPU result be compared BIT FOR BIT with this file.
+ *
+ *  libnmpc_oracle_serial.so (-DNMPC_ORACLE_SERIAL) — the same control flow with the
+ *    REFERENCE's arithmetic: libm sin/cos, true divisions, separate multiply and add (no fma),
+ *    the rollout as the literal recurrence of src/mpc/mpc_generator.py:88-90, every sum a
+ *    serial loop in ascending t.  It shares no reduction order, no sincos and no reciprocal
+ *    with the kernel: the solve-level pin that is independent of the kernel's arithmetic
+ *    (tests/test_serial_pin.py compares full solves at the north_star tolerance 1e-4).
  */
 #define _GNU_SOURCE
 #include <math.h>
@@ -46,9 +55,17 @@
 #endif
 #include "../include/nmpc_b200.h"
 
-#define LANES 32
+#define MAXG 16
 #define MAXT NMPC_MAX_HORIZON
 #define MEMP1 (NMPC_LBFGS_MAX + 1)
+
+#ifdef NMPC_ORACLE_SERIAL
+#define FMA(a, b, c) ((a) * (b) + (c))
+#define RDIV(x, d, inv) ((x) / (d))
+#else
+#define FMA(a, b, c) fma((a), (b), (c))
+#define RDIV(x, d, inv) ((x) * (inv))
+#endif
 
 /* ------------------------------------------------------------------------- */
 /* constants of OpEn's PANOC engine (panoc_engine.rs, panoc_cache.rs)          */
@@ -66,6 +83,8 @@
 #define DBL_EPS 2.220446049250313e-16 /* f64::EPSILON */
 #define Y_SET_BOUND 1e12              /* opengen SetYCalculator.LARGE_NUM */
 
+static int g_trace = 0; /* NMPC_ORACLE_TRACE, read once per batch call */
+
 /* ------------------------------------------------------------------------- */
 /* sincos: Cody-Waite reduction by pi/2 (three fma terms), fdlibm kernel
  * polynomials evaluated by Horner with fma.  Replaces the libm sin/cos calls in
@@ -82,6 +101,10 @@ static const double C1 = 4.16666666666666019037e-02, C2 = -1.3888888888874109574
                     C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
 
 void nmpc_oracle_sincos(double x, double* s, double* c) {
+#ifdef NMPC_ORACLE_SERIAL
+    *s = sin(x);
+    *c = cos(x);
+#else
     if (!(fabs(x) < 1.0e8)) { /* also catches NaN/inf: the solve reports NotFinite */
         *s = NAN;
         *c = NAN;
@@ -111,6 +134,7 @@ void nmpc_oracle_sincos(double x, double* s, double* c) {
         case 2: *s = -sr; *c = -cr; break;
         default: *s = -cr; *c = sr; break;
     }
+#endif
 }
 
 /* min/max written as compare-selects (the kernel uses the same forms): a NaN operand yields the
@@ -123,89 +147,107 @@ static inline double sel_clamp01(double t) {
 static inline double sel_excess(double z, double lo, double hi) { return (z > hi) ? z - hi : ((z < lo) ? z - lo : 0.0); }
 
 /* ------------------------------------------------------------------------- */
-/* warp-ordered reductions                                                     */
-
-/* xor-butterfly sum of 32 lane partials */
-static double tree32(double* p) {
-    for (int off = 16; off; off >>= 1)
-        for (int i = 0; i < off; i++) p[i] = p[i] + p[i + off];
-    return p[0];
+/* horizon layout of one evaluation group of the kernel: G lanes x S consecutive steps */
+void nmpc_oracle_layout(int N, int* G, int* S) {
+    if (N <= 16) { *G = 8; *S = 2; }
+    else if (N <= 24) { *G = 8; *S = 3; }
+    else if (N <= 32) { *G = 16; *S = 2; }
+    else if (N <= 48) { *G = 16; *S = 3; }
+    else if (N <= 64) { *G = 16; *S = 4; }
+    else { *G = 16; *S = 6; }
 }
 
-/* sum over the horizon of per-step values e[t]: lane partial = e[l] + e[l+32] + ...  */
-static double hsum(const double* e, int N, int P) {
-    double p[LANES];
-    for (int l = 0; l < LANES; l++) {
-        double a = (l < N) ? e[l] : 0.0;
-        for (int j = 1; j < P; j++) {
-            int t = l + LANES * j;
+/* sum over the horizon of per-step values e[t] */
+static double hsum(const double* e, int N, int G, int S) {
+#ifdef NMPC_ORACLE_SERIAL
+    (void)G; (void)S;
+    double a = 0.0;
+    for (int t = 0; t < N; t++) a = a + e[t];
+    return a;
+#else
+    double p[MAXG];
+    for (int i = 0; i < G; i++) {
+        double a = (S * i < N) ? e[S * i] : 0.0;
+        for (int s = 1; s < S; s++) {
+            int t = S * i + s;
             a = a + ((t < N) ? e[t] : 0.0);
         }
-        p[l] = a;
+        p[i] = a;
     }
-    return tree32(p);
+    for (int off = G / 2; off; off >>= 1)
+        for (int i = 0; i < off; i++) p[i] = p[i] + p[i + off];
+    return p[0];
+#endif
 }
 
-/* Kogge-Stone inclusive prefix sum along the horizon with a carry between passes */
-static void prefix_scan(const double* x, int N, int P, double* incl, double* excl) {
-    double carry = 0.0;
-    for (int j = 0; j < P; j++) {
-        double l[LANES];
-        for (int i = 0; i < LANES; i++) {
-            int t = i + LANES * j;
-            l[i] = (t < N) ? x[t] : 0.0;
+/* inclusive / exclusive prefix sums along the horizon */
+static void prefix_scan(const double* x, int N, int G, int S, double* incl, double* excl) {
+#ifdef NMPC_ORACLE_SERIAL
+    (void)G; (void)S;
+    double a = 0.0;
+    for (int t = 0; t < N; t++) { excl[t] = a; a = a + x[t]; incl[t] = a; }
+#else
+    double c[MAXT], T[MAXG], E[MAXG];
+    for (int i = 0; i < G; i++) {
+        double a = 0.0;
+        for (int s = 0; s < S; s++) {
+            int t = S * i + s;
+            double v = (t < N) ? x[t] : 0.0;
+            a = (s == 0) ? v : a + v;
+            c[t] = a;
         }
-        for (int off = 1; off < LANES; off <<= 1)
-            for (int i = LANES - 1; i >= off; i--) l[i] = l[i] + l[i - off];
-        double last = 0.0;
-        for (int i = 0; i < LANES; i++) {
-            int t = i + LANES * j;
-            double g = (j == 0) ? l[i] : carry + l[i];
-            if (t < N) {
-                incl[t] = g;
-                excl[t] = (i == 0) ? carry : ((j == 0) ? l[i - 1] : carry + l[i - 1]);
-            }
-            if (i == LANES - 1) last = g;
-        }
-        carry = last;
+        T[i] = a;
     }
+    for (int off = 1; off < G; off <<= 1)
+        for (int i = G - 1; i >= off; i--) T[i] = T[i] + T[i - off];
+    for (int i = 0; i < G; i++) E[i] = i ? T[i - 1] : 0.0;
+    for (int t = 0; t < N; t++) {
+        int i = t / S, s = t % S;
+        incl[t] = E[i] + c[t];
+        excl[t] = s ? E[i] + c[t - 1] : E[i];
+    }
+#endif
 }
 
-/* Kogge-Stone inclusive suffix sum (from the end of the horizon) */
-static void suffix_scan(const double* x, int N, int P, double* suf) {
-    double carry = 0.0;
-    for (int j = P - 1; j >= 0; j--) {
-        double l[LANES];
-        for (int i = 0; i < LANES; i++) {
-            int t = i + LANES * j;
-            l[i] = (t < N) ? x[t] : 0.0;
+/* inclusive suffix sums (from the end of the horizon) */
+static void suffix_scan(const double* x, int N, int G, int S, double* suf) {
+#ifdef NMPC_ORACLE_SERIAL
+    (void)G; (void)S;
+    double a = 0.0;
+    for (int t = N - 1; t >= 0; t--) { a = a + x[t]; suf[t] = a; }
+#else
+    double d[MAXT], T[MAXG], E[MAXG];
+    for (int i = 0; i < G; i++) {
+        double a = 0.0;
+        for (int s = S - 1; s >= 0; s--) {
+            int t = S * i + s;
+            double v = (t < N) ? x[t] : 0.0;
+            a = (s == S - 1) ? v : a + v;
+            d[t] = a;
         }
-        for (int off = 1; off < LANES; off <<= 1)
-            for (int i = 0; i + off < LANES; i++) l[i] = l[i] + l[i + off];
-        double first = 0.0;
-        for (int i = 0; i < LANES; i++) {
-            int t = i + LANES * j;
-            double g = (j == P - 1) ? l[i] : carry + l[i];
-            if (t < N) suf[t] = g;
-            if (i == 0) first = g;
-        }
-        carry = first;
+        T[i] = a;
     }
+    for (int off = 1; off < G; off <<= 1)
+        for (int i = 0; i + off < G; i++) T[i] = T[i] + T[i + off];
+    for (int i = 0; i < G; i++) E[i] = (i + 1 < G) ? T[i + 1] : 0.0;
+    for (int t = 0; t < N; t++) suf[t] = E[t / S] + d[t];
+#endif
 }
 
 /* ------------------------------------------------------------------------- */
 /* staged problem: the parameter vector unpacked once per solve                */
 typedef struct {
-    int N, Nobs, Nd, P, mem;
+    int N, Nobs, Nd, G, S, mem;
     double ts, inv_ts;
     double vmin, vmax, wmax, amin, amax, aamax;
     double x0, y0, th0, vinit, winit, xref, yref, thref;
     double q, qv, qth, rv, rw, qN, qthN, qcte, ap, wp;
     double vref[MAXT];
-    double s1x[MAXT], s1y[MAXT], sdx[MAXT], sdy[MAXT], sinv[MAXT]; /* segment i = 1..N-1 */
-    double *cx, *cy, *cr2;                       /* [Nobs]   */
-    double *ex, *ey, *eca, *esa, *eirx2, *eiry2; /* [Nd * N] index k*N + t */
+    double s1x[MAXT], s1y[MAXT], sdx[MAXT], sdy[MAXT], sden[MAXT], sinv[MAXT]; /* segment i = 1..N-1 */
+    double *cx, *cy, *cr2;                                     /* [Nobs]   */
+    double *ex, *ey, *eca, *esa, *erx2, *ery2, *eirx2, *eiry2; /* [Nd * N] index k*N + t */
     double* buf;
+    size_t buf_len;
     int n_cost, n_grad;
 } staged;
 
@@ -215,7 +257,8 @@ static int stage(staged* S, const nmpc_config* cfg, const double* p) {
     int N = cfg->N_hor, Nobs = cfg->Nobs, Nd = cfg->Ndynobs;
     if (N < 2 || N > MAXT || Nobs < 0 || Nd < 0) return 1;
     if (cfg->lbfgs_memory < 1 || cfg->lbfgs_memory > NMPC_LBFGS_MAX) return 1;
-    S->N = N; S->Nobs = Nobs; S->Nd = Nd; S->P = (N + LANES - 1) / LANES; S->mem = cfg->lbfgs_memory;
+    S->N = N; S->Nobs = Nobs; S->Nd = Nd; S->mem = cfg->lbfgs_memory;
+    nmpc_oracle_layout(N, &S->G, &S->S);
     S->ts = cfg->ts; S->inv_ts = 1.0 / cfg->ts;
     S->vmin = cfg->lin_vel_min; S->vmax = cfg->lin_vel_max; S->wmax = cfg->ang_vel_max;
     S->amin = cfg->lin_acc_min; S->amax = cfg->lin_acc_max; S->aamax = cfg->ang_acc_max;
@@ -224,13 +267,17 @@ static int stage(staged* S, const nmpc_config* cfg, const double* p) {
     S->q = p[10]; S->qv = p[11]; S->qth = p[12]; S->rv = p[13]; S->rw = p[14];
     S->qN = p[15]; S->qthN = p[16]; S->qcte = p[17]; S->ap = p[18]; S->wp = p[19];
     for (int t = 0; t < N; t++) S->vref[t] = p[NMPC_NZ + t];
-    size_t nd = (size_t)3 * Nobs + (size_t)6 * Nd * N + 8;
-    S->buf = (double*)malloc(nd * sizeof(double));
-    if (!S->buf) return 3;
+    size_t nd = (size_t)3 * Nobs + (size_t)8 * Nd * N + 8;
+    if (nd > S->buf_len) {
+        free(S->buf);
+        S->buf = (double*)malloc(nd * sizeof(double));
+        S->buf_len = S->buf ? nd : 0;
+        if (!S->buf) return 3;
+    }
     double* b = S->buf;
     S->cx = b; b += Nobs; S->cy = b; b += Nobs; S->cr2 = b; b += Nobs;
-    S->ex = b; b += Nd * N; S->ey = b; b += Nd * N; S->eca = b; b += Nd * N;
-    S->esa = b; b += Nd * N; S->eirx2 = b; b += Nd * N; S->eiry2 = b; b += Nd * N;
+    S->ex = b; b += Nd * N; S->ey = b; b += Nd * N; S->eca = b; b += Nd * N; S->esa = b; b += Nd * N;
+    S->erx2 = b; b += Nd * N; S->ery2 = b; b += Nd * N; S->eirx2 = b; b += Nd * N; S->eiry2 = b; b += Nd * N;
     const double* pc = p + NMPC_NZ + N;
     for (int k = 0; k < Nobs; k++) {
         S->cx[k] = pc[3 * k]; S->cy[k] = pc[3 * k + 1];
@@ -242,8 +289,9 @@ static int stage(staged* S, const nmpc_config* cfg, const double* p) {
             const double* e = pe + (size_t)k * 5 * N + 5 * t;
             int i = k * N + t;
             S->ex[i] = e[0]; S->ey[i] = e[1];
-            S->eirx2[i] = 1.0 / (e[2] * e[2]); /* / x_radius**2, :118 */
-            S->eiry2[i] = 1.0 / (e[3] * e[3]);
+            S->erx2[i] = e[2] * e[2]; S->ery2[i] = e[3] * e[3]; /* / x_radius**2, :118 */
+            S->eirx2[i] = 1.0 / S->erx2[i];
+            S->eiry2[i] = 1.0 / S->ery2[i];
             nmpc_oracle_sincos(e[4], &S->esa[i], &S->eca[i]);
         }
     const double* pr = pe + (size_t)5 * Nd * N;
@@ -251,13 +299,12 @@ static int stage(staged* S, const nmpc_config* cfg, const double* p) {
         double ax = pr[3 * (i - 1)], ay = pr[3 * (i - 1) + 1];
         double dx = pr[3 * i] - ax, dy = pr[3 * i + 1] - ay;
         S->s1x[i] = ax; S->s1y[i] = ay; S->sdx[i] = dx; S->sdy[i] = dy;
-        S->sinv[i] = 1.0 / (fma(dx, dx, dy * dy) + 1e-16); /* /(|s2-s1|^2 + 1e-16), :135 */
+        S->sden[i] = FMA(dx, dx, dy * dy) + 1e-16; /* |s2-s1|^2 + 1e-16, :135 */
+        S->sinv[i] = 1.0 / S->sden[i];
     }
     S->n_cost = S->n_grad = 0;
     return 0;
 }
-
-static void unstage(staged* S) { free(S->buf); S->buf = 0; }
 
 /* ------------------------------------------------------------------------- */
 /* psi(u; c, y, p) and grad psi.
@@ -273,32 +320,49 @@ static void unstage(staged* S) { free(S->buf); S->buf = 0; }
  * y is in F1 order [acc(N); omega_acc(N)].  Any output pointer may be NULL. */
 static double eval_psi(staged* S, const double* u, double c, const double* y, double* grad,
                        double* F1, double* F2) {
-    const int N = S->N, P = S->P;
+    const int N = S->N, G = S->G, SS = S->S;
     const double ts = S->ts, inv_ts = S->inv_ts;
-    const double hc = 0.5 * c, inv_c = 1.0 / fmax(c, 1.0);
-    double tw[MAXT] = {0}, inclT[MAXT], exclT[MAXT], sn[MAXT], cs[MAXT], a[MAXT] = {0}, b[MAXT] = {0};
-    double inclA[MAXT], exclA[MAXT], inclB[MAXT], exclB[MAXT];
+    const double hc = 0.5 * c, cden = fmax(c, 1.0), inv_c = 1.0 / cden;
+    double sn[MAXT], cs[MAXT];
     double X[MAXT], Y[MAXT], TH[MAXT], thpre[MAXT], xpre[MAXT], ypre[MAXT];
     double gX[MAXT], gY[MAXT], mind2[MAXT], cl[MAXT], Aa[MAXT], Aw[MAXT];
-    double h[MAXT], hdx[MAXT], hdy[MAXT];
+    double h[MAXT], hp[MAXT], hdx[MAXT], hdy[MAXT];
     if (grad) S->n_grad++; else S->n_cost++;
 
     /* rollout x += ts*(v*cos th); y += ts*(v*sin th); th += ts*w   (:88-90) */
-    for (int t = 0; t < N; t++) tw[t] = ts * u[2 * t + 1];
-    prefix_scan(tw, N, P, inclT, exclT);
-    for (int t = 0; t < N; t++) {
-        thpre[t] = S->th0 + exclT[t];
-        TH[t] = S->th0 + inclT[t];
-        nmpc_oracle_sincos(thpre[t], &sn[t], &cs[t]);
-        a[t] = ts * (u[2 * t] * cs[t]);
-        b[t] = ts * (u[2 * t] * sn[t]);
+#ifdef NMPC_ORACLE_SERIAL
+    {
+        double x = S->x0, yy = S->y0, th = S->th0;
+        for (int t = 0; t < N; t++) {
+            xpre[t] = x; ypre[t] = yy; thpre[t] = th;
+            nmpc_oracle_sincos(th, &sn[t], &cs[t]);
+            x = x + ts * (u[2 * t] * cs[t]);
+            yy = yy + ts * (u[2 * t] * sn[t]);
+            th = th + ts * u[2 * t + 1];
+            X[t] = x; Y[t] = yy; TH[t] = th;
+        }
     }
-    prefix_scan(a, N, P, inclA, exclA);
-    prefix_scan(b, N, P, inclB, exclB);
-    for (int t = 0; t < N; t++) {
-        xpre[t] = S->x0 + exclA[t]; ypre[t] = S->y0 + exclB[t];
-        X[t] = S->x0 + inclA[t];    Y[t] = S->y0 + inclB[t];
+#else
+    {
+        double tw[MAXT], a[MAXT], b[MAXT], inclT[MAXT], exclT[MAXT];
+        double inclA[MAXT], exclA[MAXT], inclB[MAXT], exclB[MAXT];
+        for (int t = 0; t < N; t++) tw[t] = ts * u[2 * t + 1];
+        prefix_scan(tw, N, G, SS, inclT, exclT);
+        for (int t = 0; t < N; t++) {
+            thpre[t] = S->th0 + exclT[t];
+            TH[t] = S->th0 + inclT[t];
+            nmpc_oracle_sincos(thpre[t], &sn[t], &cs[t]);
+            a[t] = ts * (u[2 * t] * cs[t]);
+            b[t] = ts * (u[2 * t] * sn[t]);
+        }
+        prefix_scan(a, N, G, SS, inclA, exclA);
+        prefix_scan(b, N, G, SS, inclB, exclB);
+        for (int t = 0; t < N; t++) {
+            xpre[t] = S->x0 + exclA[t]; ypre[t] = S->y0 + exclB[t];
+            X[t] = S->x0 + inclA[t];    Y[t] = S->y0 + inclB[t];
+        }
     }
+#endif
 
     /* cross-track error: min over segments of squared distance (:122-144) */
     for (int t = 0; t < N; t++) {
@@ -306,64 +370,73 @@ static double eval_psi(staged* S, const double* u, double c, const double* y, do
         int bi = 1;
         for (int i = 1; i < N; i++) {
             double px = X[t] - S->s1x[i], py = Y[t] - S->s1y[i];
-            double that = fma(px, S->sdx[i], py * S->sdy[i]) * S->sinv[i];
+            double that = RDIV(FMA(px, S->sdx[i], py * S->sdy[i]), S->sden[i], S->sinv[i]);
             double tst = sel_clamp01(that); /* fmin(fmax(t_hat, 0), 1), :138 */
+#ifdef NMPC_ORACLE_SERIAL
+            double ex = S->s1x[i] + tst * S->sdx[i] - X[t], ey = S->s1y[i] + tst * S->sdy[i] - Y[t]; /* temp_vec, :140 */
+#else
             double ex = fma(tst, S->sdx[i], -px), ey = fma(tst, S->sdy[i], -py);
-            double d2 = fma(ex, ex, ey * ey);
+#endif
+            double d2 = FMA(ex, ex, ey * ey);
             if (d2 < best) { best = d2; bi = i; bex = ex; bey = ey; bth = that; }
         }
         mind2[t] = best;
         if (grad) {
-            double ed = (bth >= 0.0 && bth <= 1.0) ? fma(bex, S->sdx[bi], bey * S->sdy[bi]) * S->sinv[bi] : 0.0;
+            double ed = (bth >= 0.0 && bth <= 1.0) ? RDIV(FMA(bex, S->sdx[bi], bey * S->sdy[bi]), S->sden[bi], S->sinv[bi]) : 0.0;
             double k2 = 2.0 * S->qcte;
-            gX[t] = k2 * fma(ed, S->sdx[bi], -bex);
-            gY[t] = k2 * fma(ed, S->sdy[bi], -bey);
+            gX[t] = k2 * FMA(ed, S->sdx[bi], -bex);
+            gY[t] = k2 * FMA(ed, S->sdy[bi], -bey);
         }
     }
 
-    /* obstacle penalty F2 (:106-119): circles then ellipses */
+    /* obstacle penalty F2 (:106-119): circles then ellipses; F2_k = sum over the horizon of max(0, inside) */
     double pen = 0.0;
     for (int k = 0; k < S->Nobs; k++) {
-        double g = 0.0;
         for (int t = 0; t < N; t++) {
             hdx[t] = X[t] - S->cx[k]; hdy[t] = Y[t] - S->cy[k];
-            h[t] = fma(-hdy[t], hdy[t], fma(-hdx[t], hdx[t], S->cr2[k]));
-            if (h[t] > 0.0) g = g + h[t];
+            h[t] = FMA(-hdy[t], hdy[t], FMA(-hdx[t], hdx[t], S->cr2[k]));
+            hp[t] = (h[t] > 0.0) ? h[t] : 0.0;
         }
+        double g = hsum(hp, N, G, SS);
         if (F2) F2[k] = g;
-        pen = fma(g, g, pen);
+        pen = FMA(g, g, pen);
         if (grad && g > 0.0) {
             double cg = c * g;
             for (int t = 0; t < N; t++)
                 if (h[t] > 0.0) {
-                    gX[t] = fma(cg, -2.0 * hdx[t], gX[t]);
-                    gY[t] = fma(cg, -2.0 * hdy[t], gY[t]);
+                    gX[t] = FMA(cg, -2.0 * hdx[t], gX[t]);
+                    gY[t] = FMA(cg, -2.0 * hdy[t], gY[t]);
                 }
         }
     }
     for (int k = 0; k < S->Nd; k++) {
-        double g = 0.0;
         double ta[MAXT], tb[MAXT];
         for (int t = 0; t < N; t++) {
             int i = k * N + t;
             double dx = X[t] - S->ex[i], dy = Y[t] - S->ey[i];
-            double ea = fma(dx, S->eca[i], dy * S->esa[i]);
-            double eb = fma(dx, S->esa[i], -(dy * S->eca[i]));
+            double ea = FMA(dx, S->eca[i], dy * S->esa[i]);
+            double eb = FMA(dx, S->esa[i], -(dy * S->eca[i]));
+#ifdef NMPC_ORACLE_SERIAL
+            h[t] = 1.0 - (ea * ea) / S->erx2[i] - (eb * eb) / S->ery2[i];
+            ta[t] = ea / S->erx2[i]; tb[t] = eb / S->ery2[i];
+#else
             h[t] = fma(-(eb * eb), S->eiry2[i], fma(-(ea * ea), S->eirx2[i], 1.0));
             ta[t] = ea * S->eirx2[i]; tb[t] = eb * S->eiry2[i];
-            if (h[t] > 0.0) g = g + h[t];
+#endif
+            hp[t] = (h[t] > 0.0) ? h[t] : 0.0;
         }
+        double g = hsum(hp, N, G, SS);
         if (F2) F2[S->Nobs + k] = g;
-        pen = fma(g, g, pen);
+        pen = FMA(g, g, pen);
         if (grad && g > 0.0) {
             double cg = c * g;
             for (int t = 0; t < N; t++)
                 if (h[t] > 0.0) {
                     int i = k * N + t;
-                    double hX = -2.0 * fma(ta[t], S->eca[i], tb[t] * S->esa[i]);
-                    double hY = -2.0 * fma(ta[t], S->esa[i], -(tb[t] * S->eca[i]));
-                    gX[t] = fma(cg, hX, gX[t]);
-                    gY[t] = fma(cg, hY, gY[t]);
+                    double hX = -2.0 * FMA(ta[t], S->eca[i], tb[t] * S->esa[i]);
+                    double hY = -2.0 * FMA(ta[t], S->esa[i], -(tb[t] * S->eca[i]));
+                    gX[t] = FMA(cg, hX, gX[t]);
+                    gY[t] = FMA(cg, hY, gY[t]);
                 }
         }
     }
@@ -373,69 +446,74 @@ static double eval_psi(staged* S, const double* u, double c, const double* y, do
         double v = u[2 * t], w = u[2 * t + 1];
         double vp = t ? u[2 * t - 2] : S->vinit, wp_ = t ? u[2 * t - 1] : S->winit;
         double c0 = S->rv * (v * v);
-        c0 = fma(S->rw, w * w, c0);
+        c0 = FMA(S->rw, w * w, c0);
         double dv = v - S->vref[t];
-        c0 = fma(S->qv, dv * dv, c0);
+        c0 = FMA(S->qv, dv * dv, c0);
         double ex = xpre[t] - S->xref, ey = ypre[t] - S->yref, et = thpre[t] - S->thref;
-        c0 = fma(S->q, fma(ex, ex, ey * ey), c0);
-        c0 = fma(S->qth, et * et, c0);
-        c0 = fma(S->qcte, mind2[t], c0);
-        double acc = (v - vp) * inv_ts, aac = (w - wp_) * inv_ts;
-        c0 = fma(S->ap, acc * acc, c0);
-        c0 = fma(S->wp, aac * aac, c0);
+        c0 = FMA(S->q, FMA(ex, ex, ey * ey), c0);
+        c0 = FMA(S->qth, et * et, c0);
+        c0 = FMA(S->qcte, mind2[t], c0);
+        double acc = RDIV(v - vp, ts, inv_ts), aac = RDIV(w - wp_, ts, inv_ts);
+        c0 = FMA(S->ap, acc * acc, c0);
+        c0 = FMA(S->wp, aac * aac, c0);
+#ifdef NMPC_ORACLE_SERIAL
+        double za = acc + (y ? y[t] : 0.0) / cden, zw = aac + (y ? y[N + t] : 0.0) / cden;
+#else
         double za = fma(y ? y[t] : 0.0, inv_c, acc), zw = fma(y ? y[N + t] : 0.0, inv_c, aac);
+#endif
         double da = sel_excess(za, S->amin, S->amax);   /* z - Proj_C(z) */
         double dw = sel_excess(zw, -S->aamax, S->aamax);
-        c0 = fma(hc, fma(da, da, dw * dw), c0);
+        c0 = FMA(hc, FMA(da, da, dw * dw), c0);
         cl[t] = c0;
-        Aa[t] = fma(c, da, (2.0 * S->ap) * acc) * inv_ts;
-        Aw[t] = fma(c, dw, (2.0 * S->wp) * aac) * inv_ts;
+        Aa[t] = RDIV(FMA(c, da, (2.0 * S->ap) * acc), ts, inv_ts);
+        Aw[t] = RDIV(FMA(c, dw, (2.0 * S->wp) * aac), ts, inv_ts);
         if (F1) { F1[t] = acc; F1[N + t] = aac; }
     }
+    (void)inv_c;
     /* terminal cost (:148) */
     double eXN = X[N - 1] - S->xref, eYN = Y[N - 1] - S->yref, eTN = TH[N - 1] - S->thref;
-    double term = fma(S->qN, fma(eXN, eXN, eYN * eYN), S->qthN * (eTN * eTN));
-    double psi = fma(hc, pen, hsum(cl, N, P) + term);
+    double term = FMA(S->qN, FMA(eXN, eXN, eYN * eYN), S->qthN * (eTN * eTN));
+    double psi = FMA(hc, pen, hsum(cl, N, G, SS) + term);
     if (!grad) return psi;
 
     /* backward sweep */
-    double mth[MAXT], LX[MAXT], LY[MAXT], nn[MAXT], rr[MAXT] = {0}, TT[MAXT];
+    double mth[MAXT], LX[MAXT], LY[MAXT], nn[MAXT], rr[MAXT], TT[MAXT];
     for (int t = 0; t < N; t++) {
         double qq = (t + 1 < N) ? S->q : S->qN, qt = (t + 1 < N) ? S->qth : S->qthN;
-        gX[t] = fma(2.0 * qq, X[t] - S->xref, gX[t]);
-        gY[t] = fma(2.0 * qq, Y[t] - S->yref, gY[t]);
+        gX[t] = FMA(2.0 * qq, X[t] - S->xref, gX[t]);
+        gY[t] = FMA(2.0 * qq, Y[t] - S->yref, gY[t]);
         mth[t] = (2.0 * qt) * (TH[t] - S->thref);
     }
-    suffix_scan(gX, N, P, LX);
-    suffix_scan(gY, N, P, LY);
-    for (int t = 0; t < N; t++) nn[t] = (ts * u[2 * t]) * fma(cs[t], LY[t], -(sn[t] * LX[t]));
+    suffix_scan(gX, N, G, SS, LX);
+    suffix_scan(gY, N, G, SS, LY);
+    for (int t = 0; t < N; t++) nn[t] = (ts * u[2 * t]) * FMA(cs[t], LY[t], -(sn[t] * LX[t]));
     for (int t = 0; t < N; t++) rr[t] = mth[t] + ((t + 1 < N) ? nn[t + 1] : 0.0);
-    suffix_scan(rr, N, P, TT);
+    suffix_scan(rr, N, G, SS, TT);
     for (int t = 0; t < N; t++) {
         double v = u[2 * t], w = u[2 * t + 1];
         double An = (t + 1 < N) ? Aa[t + 1] : 0.0, Wn = (t + 1 < N) ? Aw[t + 1] : 0.0;
-        double lv = fma(2.0 * S->rv, v, (2.0 * S->qv) * (v - S->vref[t])) + (Aa[t] - An);
+        double lv = FMA(2.0 * S->rv, v, (2.0 * S->qv) * (v - S->vref[t])) + (Aa[t] - An);
         double lw = (2.0 * S->rw) * w + (Aw[t] - Wn);
-        grad[2 * t] = fma(ts, fma(cs[t], LX[t], sn[t] * LY[t]), lv);
-        grad[2 * t + 1] = fma(ts, TT[t], lw);
+        grad[2 * t] = FMA(ts, FMA(cs[t], LX[t], sn[t] * LY[t]), lv);
+        grad[2 * t + 1] = FMA(ts, TT[t], lw);
     }
     return psi;
 }
 
 /* ------------------------------------------------------------------------- */
-/* vector helpers on interleaved 2N vectors, lane-pair partials                */
-static double vdot(const double* a, const double* b, int N, int P) {
+/* vector helpers on interleaved 2N vectors: per-step partial, then the horizon sum */
+static double vdot(const staged* S, const double* a, const double* b) {
     double e[MAXT];
-    for (int t = 0; t < N; t++) e[t] = fma(a[2 * t + 1], b[2 * t + 1], a[2 * t] * b[2 * t]);
-    return hsum(e, N, P);
+    for (int t = 0; t < S->N; t++) e[t] = FMA(a[2 * t + 1], b[2 * t + 1], a[2 * t] * b[2 * t]);
+    return hsum(e, S->N, S->G, S->S);
 }
-static double vdiff2(const double* a, const double* b, int N, int P) { /* |a-b|^2 */
+static double vdiff2(const staged* S, const double* a, const double* b) { /* |a-b|^2 */
     double e[MAXT];
-    for (int t = 0; t < N; t++) {
+    for (int t = 0; t < S->N; t++) {
         double d0 = a[2 * t] - b[2 * t], d1 = a[2 * t + 1] - b[2 * t + 1];
-        e[t] = fma(d1, d1, d0 * d0);
+        e[t] = FMA(d1, d1, d0 * d0);
     }
-    return hsum(e, N, P);
+    return hsum(e, S->N, S->G, S->S);
 }
 static int all_finite(const double* a, int n) {
     for (int i = 0; i < n; i++)
@@ -449,12 +527,11 @@ static int all_finite(const double* a, int n) {
  * (cbfgs alpha 1, cbfgs epsilon 1e-8, sy epsilon 1e-10).  Slot 0 is the newest
  * pair; the extra slot is the staging area that rotate_right(1) moves to the front. */
 typedef struct {
-    int n2, N, P, mem, active, first_old, head;
+    const staged* S;
+    int n2, mem, active, first_old, head;
     double lgamma;
     double s[MEMP1][2 * MAXT], y[MEMP1][2 * MAXT];
     double rho[MEMP1], alpha[NMPC_LBFGS_MAX];
-    double SY[MEMP1][MEMP1], YY[MEMP1][MEMP1]; /* Gram entries s_p.y_q, y_p.y_q by physical slot */
-    int two_loop;                               /* 1 (default): literal two-loop recursion; 0: compact form */
     double old_state[2 * MAXT], old_g[2 * MAXT];
 } lbfgs_t;
 
@@ -473,87 +550,37 @@ static void lb_update(lbfgs_t* L, const double* g, const double* state) {
     double* s = L->s[tmp];
     double* y = L->y[tmp];
     for (int i = 0; i < n2; i++) { s[i] = state[i] - L->old_state[i]; y[i] = g[i] - L->old_g[i]; }
-    double ys = vdot(s, y, L->N, L->P);
-    double ss = vdot(s, s, L->N, L->P);
+    double ys = vdot(L->S, s, y);
+    double ss = vdot(L->S, s, s);
     L->rho[tmp] = 1.0 / ys;
     if (ss <= DBL_EPS || ys <= SY_EPSILON) return; /* rejection */
     double lhs = ys / ss;
-    double rhs = CBFGS_EPSILON * sqrt(vdot(g, g, L->N, L->P)); /* eps * |g|^alpha, alpha = 1 */
+    double rhs = CBFGS_EPSILON * sqrt(vdot(L->S, g, g)); /* eps * |g|^alpha, alpha = 1 */
     if (!(lhs > rhs && isfinite(lhs) && isfinite(rhs))) return;
     memcpy(L->old_state, state, n2 * sizeof(double));
     memcpy(L->old_g, g, n2 * sizeof(double));
-    /* Gram rows/columns of the new pair against the pairs currently held (compact form, see lb_apply) */
-    double yy = vdot(y, y, L->N, L->P);
-    for (int k = 0; k < L->active; k++) {
-        int p = lb_slot(L, k);
-        L->SY[tmp][p] = vdot(s, L->y[p], L->N, L->P);
-        L->SY[p][tmp] = vdot(L->s[p], y, L->N, L->P);
-        double v = vdot(y, L->y[p], L->N, L->P);
-        L->YY[tmp][p] = v;
-        L->YY[p][tmp] = v;
-    }
-    L->SY[tmp][tmp] = ys;
-    L->YY[tmp][tmp] = yy;
+    double yy = vdot(L->S, y, y);
     L->head = (L->head + L->mem) % (L->mem + 1); /* rotate_right(1): staging slot becomes slot 0 */
     L->lgamma = (1.0 / L->rho[tmp]) / yy;
     L->active = (L->active + 1 < L->mem) ? L->active + 1 : L->mem;
 }
 
-/* literal two-loop recursion of the lbfgs crate (Lbfgs::apply_hessian): 2*active sequential reductions.
- * This is the arithmetic contract shared with the kernel. */
-static void lb_apply_two_loop(lbfgs_t* L, double* q) {
+/* literal two-loop recursion of the lbfgs crate (Lbfgs::apply_hessian): 2*active sequential reductions */
+static void lb_apply(lbfgs_t* L, double* q) {
     const int n2 = L->n2;
+    if (L->active == 0) return; /* empty buffer: H = I */
     for (int k = 0; k < L->active; k++) {
         int sl = lb_slot(L, k);
-        double al = L->rho[sl] * vdot(L->s[sl], q, L->N, L->P);
+        double al = L->rho[sl] * vdot(L->S, L->s[sl], q);
         L->alpha[k] = al;
-        for (int i = 0; i < n2; i++) q[i] = fma(-al, L->y[sl][i], q[i]);
+        for (int i = 0; i < n2; i++) q[i] = FMA(-al, L->y[sl][i], q[i]);
     }
     for (int i = 0; i < n2; i++) q[i] = q[i] * L->lgamma;
     for (int k = L->active - 1; k >= 0; k--) {
         int sl = lb_slot(L, k);
-        double beta = L->rho[sl] * vdot(L->y[sl], q, L->N, L->P);
+        double beta = L->rho[sl] * vdot(L->S, L->y[sl], q);
         double co = L->alpha[k] - beta;
-        for (int i = 0; i < n2; i++) q[i] = fma(co, L->s[sl][i], q[i]);
-    }
-}
-
-/* Lbfgs::apply_hessian in compact form — an ALTERNATIVE evaluation order kept for sensitivity tests
- * (NMPC_ORACLE_COMPACT=1) and for experiments/nmpc_device_compact_lbfgs.cuh; NOT the default.  Same two-loop
- * recursion, but every inner product is taken against the ORIGINAL g and the stored pairs, so they are all
- * independent (one batched warp reduction on the GPU) and the recursion itself runs on scalars:
- *   alpha_i = rho_i (s_i.g - sum_{j<i} alpha_j s_i.y_j)
- *   beta_i  = rho_i (gamma (y_i.g - sum_j alpha_j y_i.y_j) + sum_{l>i} c_l s_l.y_i),   c_i = alpha_i - beta_i
- *   d       = gamma g - sum_j gamma alpha_j y_j + sum_l c_l s_l
- * Mathematically identical to lb_apply_two_loop; differs in rounding only. */
-static void lb_apply(lbfgs_t* L, double* q) {
-    if (L->active == 0) return;
-    if (L->two_loop) { lb_apply_two_loop(L, q); return; }
-    const int n2 = L->n2, k = L->active;
-    int p[NMPC_LBFGS_MAX];
-    double a[NMPC_LBFGS_MAX], b[NMPC_LBFGS_MAX], al[NMPC_LBFGS_MAX], c[NMPC_LBFGS_MAX];
-    for (int i = 0; i < k; i++) {
-        p[i] = lb_slot(L, i);
-        a[i] = vdot(L->s[p[i]], q, L->N, L->P);
-        b[i] = vdot(L->y[p[i]], q, L->N, L->P);
-    }
-    for (int i = 0; i < k; i++) {
-        double acc = a[i];
-        for (int j = 0; j < i; j++) acc = fma(-al[j], L->SY[p[i]][p[j]], acc);
-        al[i] = L->rho[p[i]] * acc;
-    }
-    for (int i = k - 1; i >= 0; i--) {
-        double t = b[i];
-        for (int j = 0; j < k; j++) t = fma(-al[j], L->YY[p[i]][p[j]], t);
-        t = L->lgamma * t;
-        for (int l = k - 1; l > i; l--) t = fma(c[l], L->SY[p[l]][p[i]], t);
-        c[i] = al[i] - L->rho[p[i]] * t;
-    }
-    for (int e = 0; e < n2; e++) {
-        double acc = L->lgamma * q[e];
-        for (int j = 0; j < k; j++) acc = fma(-(L->lgamma * al[j]), L->y[p[j]][e], acc);
-        for (int l = k - 1; l >= 0; l--) acc = fma(c[l], L->s[p[l]][e], acc);
-        q[e] = acc;
+        for (int i = 0; i < n2; i++) q[i] = FMA(co, L->s[sl][i], q[i]);
     }
 }
 
@@ -581,7 +608,7 @@ static void project_U(const staged* S, double* v) { /* Rectangle U, src/mpc/mpc_
     }
 }
 static void grad_step_half(panoc_t* C, const double* u) { /* gradient_step() + half_step() */
-    for (int i = 0; i < C->n2; i++) { C->gstep[i] = fma(-C->gamma, C->grad[i], u[i]); C->uhalf[i] = C->gstep[i]; }
+    for (int i = 0; i < C->n2; i++) { C->gstep[i] = FMA(-C->gamma, C->grad[i], u[i]); C->uhalf[i] = C->gstep[i]; }
     project_U(C->S, C->uhalf);
 }
 static void compute_fpr(panoc_t* C, const double* u) {
@@ -589,15 +616,15 @@ static void compute_fpr(panoc_t* C, const double* u) {
     for (int t = 0; t < C->S->N; t++) {
         double d0 = u[2 * t] - C->uhalf[2 * t], d1 = u[2 * t + 1] - C->uhalf[2 * t + 1];
         C->fpr[2 * t] = d0; C->fpr[2 * t + 1] = d1;
-        e[t] = fma(d1, d1, d0 * d0);
+        e[t] = FMA(d1, d1, d0 * d0);
     }
-    C->norm_fpr = sqrt(hsum(e, C->S->N, C->S->P));
+    C->norm_fpr = sqrt(hsum(e, C->S->N, C->S->G, C->S->S));
 }
 static void set_gamma(panoc_t* C, double g) { C->gamma = g; C->inv_gamma = 1.0 / g; }
 
 static void panoc_init(panoc_t* C, double* u) {
     staged* S = C->S;
-    const int N = S->N, P = S->P, n2 = C->n2;
+    const int N = S->N, n2 = C->n2;
     lb_reset(&C->lb);
     C->tau = 1.0; C->iteration = 0;
     /* cost and gradient at u; estimate_loc_lip perturbs u by h and LEAVES it perturbed */
@@ -607,11 +634,11 @@ static void panoc_init(panoc_t* C, double* u) {
         double e_ = EPSILON_LIPSCHITZ * u[i];
         hv[i] = (e_ > DELTA_LIPSCHITZ) ? e_ : DELTA_LIPSCHITZ; /* max{delta, epsilon*u} */
     }
-    for (int t = 0; t < N; t++) e[t] = fma(hv[2 * t + 1], hv[2 * t + 1], hv[2 * t] * hv[2 * t]);
-    double norm_h = sqrt(hsum(e, N, P));
+    for (int t = 0; t < N; t++) e[t] = FMA(hv[2 * t + 1], hv[2 * t + 1], hv[2 * t] * hv[2 * t]);
+    double norm_h = sqrt(hsum(e, N, S->G, S->S));
     for (int i = 0; i < n2; i++) u[i] = u[i] + hv[i];
     eval_psi(S, u, C->c, C->y, gh, 0, 0);
-    C->lip = sqrt(vdiff2(gh, C->grad, N, P)) / norm_h;
+    C->lip = sqrt(vdiff2(S, gh, C->grad)) / norm_h;
     set_gamma(C, GAMMA_L_COEFF / fmax(C->lip, MIN_L_ESTIMATE));
     C->sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * C->gamma);
     grad_step_half(C, u);
@@ -620,7 +647,7 @@ static void panoc_init(panoc_t* C, double* u) {
 /* returns 1 to continue, 0 when the exit condition holds */
 static int panoc_step(panoc_t* C, double* u) {
     staged* S = C->S;
-    const int N = S->N, P = S->P, n2 = C->n2;
+    const int N = S->N, n2 = C->n2;
     compute_fpr(C, u);
     /* exit_condition(): |gamma*fpr| < tol  AND  akkt residual < eps_nu.
      * akkt_residual = | fpr/gamma + df - df_prev | where cache_previous_gradient()
@@ -630,18 +657,23 @@ static int panoc_step(panoc_t* C, double* u) {
         for (int t = 0; t < N; t++) {
             double g0 = C->grad[2 * t], g1 = C->grad[2 * t + 1];
             double p0 = C->iteration ? g0 : 0.0, p1 = C->iteration ? g1 : 0.0;
+#ifdef NMPC_ORACLE_SERIAL
+            double r0 = C->fpr[2 * t] / C->gamma + g0 - p0;
+            double r1 = C->fpr[2 * t + 1] / C->gamma + g1 - p1;
+#else
             double r0 = fma(C->fpr[2 * t], C->inv_gamma, g0) - p0;
             double r1 = fma(C->fpr[2 * t + 1], C->inv_gamma, g1) - p1;
-            e[t] = fma(r1, r1, r0 * r0);
+#endif
+            e[t] = FMA(r1, r1, r0 * r0);
         }
-        if (sqrt(hsum(e, N, P)) < C->akkt_tol) return 0;
+        if (sqrt(hsum(e, N, S->G, S->S)) < C->akkt_tol) return 0;
     }
     /* update_lipschitz_constant() */
     double cost_half = eval_psi(S, C->uhalf, C->c, C->y, 0, 0, 0);
     C->cost = eval_psi(S, u, C->c, C->y, 0, 0, 0);
     int it = 0;
     for (;;) {
-        double ip = vdot(C->grad, C->fpr, N, P);
+        double ip = vdot(S, C->grad, C->fpr);
         double rhs = C->cost + LIPSCHITZ_UPDATE_EPSILON * fabs(C->cost) - ip +
                      (GAMMA_L_COEFF * 0.5 * C->inv_gamma) * (C->norm_fpr * C->norm_fpr);
         if (!(cost_half > rhs && it < MAX_LIPSCHITZ_UPDATE_ITERATIONS && C->lip < MAX_LIPSCHITZ_CONSTANT)) break;
@@ -665,25 +697,25 @@ static int panoc_step(panoc_t* C, double* u) {
         C->cost = eval_psi(S, u, C->c, C->y, C->grad, 0, 0);
         grad_step_half(C, u);
     } else { /* linesearch(): FBE decrease; up to MAX+1 trial points, the last is kept */
-        double dist2 = vdiff2(C->gstep, C->uhalf, N, P);
-        double fbe = C->cost - (0.5 * C->gamma) * vdot(C->grad, C->grad, N, P) + (0.5 * dist2) * C->inv_gamma;
+        double dist2 = vdiff2(S, C->gstep, C->uhalf);
+        double fbe = C->cost - (0.5 * C->gamma) * vdot(S, C->grad, C->grad) + (0.5 * dist2) * C->inv_gamma;
         double rhs_ls = fbe - C->sigma * (C->norm_fpr * C->norm_fpr);
         C->tau = 1.0;
         int nls = 0;
         for (;;) {
             double om = 1.0 - C->tau;
-            for (int i = 0; i < n2; i++) C->uplus[i] = fma(-C->tau, C->dir[i], fma(-om, C->fpr[i], u[i]));
+            for (int i = 0; i < n2; i++) C->uplus[i] = FMA(-C->tau, C->dir[i], FMA(-om, C->fpr[i], u[i]));
             C->cost = eval_psi(S, C->uplus, C->c, C->y, C->grad, 0, 0);
             grad_step_half(C, C->uplus);
-            double d2 = vdiff2(C->gstep, C->uhalf, N, P);
-            double lhs = C->cost - (0.5 * C->gamma) * vdot(C->grad, C->grad, N, P) + (0.5 * d2) * C->inv_gamma;
+            double d2 = vdiff2(S, C->gstep, C->uhalf);
+            double lhs = C->cost - (0.5 * C->gamma) * vdot(S, C->grad, C->grad) + (0.5 * d2) * C->inv_gamma;
             if (!(lhs > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
             C->tau /= 2.0;
             nls++;
         }
         memcpy(u, C->uplus, n2 * sizeof(double));
     }
-    if (getenv("NMPC_ORACLE_TRACE"))
+    if (g_trace)
         fprintf(stderr, "it %d cost %.12e nfpr %.3e gamma %.3e tau %.3e active %d lip %.3e\n", C->iteration, C->cost,
                 C->norm_fpr, C->gamma, C->tau, C->lb.active, C->lip);
     C->iteration++;
@@ -708,25 +740,48 @@ static int panoc_solve(panoc_t* C, double* u, int max_iter, int* iters) {
 }
 
 /* ------------------------------------------------------------------------- */
+/* per-thread workspace: nothing is allocated inside a solve */
+typedef struct {
+    staged S;
+    panoc_t C;
+    double* F2;
+    size_t F2_len;
+} workspace;
+
+static workspace* ws_new(void) { return (workspace*)calloc(1, sizeof(workspace)); }
+static void ws_free(workspace* w) {
+    if (!w) return;
+    free(w->S.buf);
+    free(w->F2);
+    free(w);
+}
+
 /* ALM / penalty outer loop — restates AlmOptimizer::{solve, step,
  * update_lagrange_multipliers, is_exit_criterion_satisfied,
  * is_penalty_stall_criterion, final_cache_update} (alm/alm_optimizer.rs) with the
  * settings the generated optimizer.rs passes (opengen 0.6.4 defaults). */
-int nmpc_oracle_solve(const nmpc_config* cfg, const double* p, double* u, double* y, nmpc_stats* st) {
-    staged S;
-    int rc = stage(&S, cfg, p);
+static int solve_ws(workspace* W, const nmpc_config* cfg, const double* p, double* u, double* y, nmpc_stats* st) {
+    staged* S = &W->S;
+    int rc = stage(S, cfg, p);
     if (rc) return -rc;
-    const int N = S.N, P = S.P, n2 = 2 * N;
-    panoc_t* C = (panoc_t*)calloc(1, sizeof(panoc_t));
+    const int N = S->N, n2 = 2 * N;
+    panoc_t* C = &W->C;
     double yp[2 * MAXT], w[2 * MAXT], ybuf[2 * MAXT];
-    double* F2 = (double*)calloc((size_t)S.Nobs + S.Nd + 1, sizeof(double));
+    size_t nf2 = (size_t)S->Nobs + S->Nd + 1;
+    if (nf2 > W->F2_len) {
+        free(W->F2);
+        W->F2 = (double*)malloc(nf2 * sizeof(double));
+        W->F2_len = W->F2 ? nf2 : 0;
+        if (!W->F2) return -3;
+    }
+    double* F2 = W->F2;
     if (!y) { memset(ybuf, 0, sizeof(ybuf)); y = ybuf; }
-    C->S = &S; C->n2 = n2; C->y = y;
-    C->lb.n2 = n2; C->lb.N = N; C->lb.P = P; C->lb.mem = S.mem; C->lb.head = 0;
-    C->lb.two_loop = getenv("NMPC_ORACLE_COMPACT") == NULL; /* default: the literal two-loop recursion */
+    C->S = S; C->n2 = n2; C->y = y;
+    C->lb.S = S; C->lb.n2 = n2; C->lb.mem = S->mem; C->lb.head = 0;
     C->tol = cfg->tolerance;
     C->c = cfg->initial_penalty;
     C->akkt_tol = cfg->initial_tolerance;
+    C->norm_fpr = 0.0;
     int iteration = 0, inner_total = 0, num_outer = 0, status = NMPC_CONVERGED, done = 0;
     double f2n = 0.0, f2np = 0.0, dyn = 0.0, dynp = 0.0;
     for (int outer = 0; outer < cfg->max_outer_iterations; outer++) {
@@ -738,24 +793,24 @@ int nmpc_oracle_solve(const nmpc_config* cfg, const double* p, double* u, double
         if (inner == NMPC_NOT_FINITE) { status = NMPC_NOT_FINITE; done = 2; break; }
         status = inner;
         /* y+ = y + c*(F1(u) - Proj_C(F1(u) + y/c)) ; F2(u) */
-        eval_psi(&S, u, 0.0, 0, 0, w, F2);
-        S.n_cost--; /* F1/F2 mappings, not a psi evaluation */
+        eval_psi(S, u, 0.0, 0, 0, w, F2);
+        S->n_cost--; /* F1/F2 mappings, not a psi evaluation */
         double e[MAXT];
         for (int t = 0; t < N; t++) {
             double za = w[t] + y[t] / C->c, zw = w[N + t] + y[N + t] / C->c;
-            za = clampd(za, S.amin, S.amax);
-            zw = clampd(zw, -S.aamax, S.aamax);
-            yp[t] = fma(C->c, w[t] - za, y[t]);
-            yp[N + t] = fma(C->c, w[N + t] - zw, y[N + t]);
+            za = clampd(za, S->amin, S->amax);
+            zw = clampd(zw, -S->aamax, S->aamax);
+            yp[t] = FMA(C->c, w[t] - za, y[t]);
+            yp[N + t] = FMA(C->c, w[N + t] - zw, y[N + t]);
             double d0 = yp[t] - y[t], d1 = yp[N + t] - y[N + t];
-            e[t] = fma(d1, d1, d0 * d0);
+            e[t] = FMA(d1, d1, d0 * d0);
         }
-        dynp = sqrt(hsum(e, N, P));
+        dynp = sqrt(hsum(e, N, S->G, S->S));
         double acc = 0.0;
-        for (int k = 0; k < S.Nobs + S.Nd; k++) acc = fma(F2[k], F2[k], acc);
+        for (int k = 0; k < S->Nobs + S->Nd; k++) acc = FMA(F2[k], F2[k], acc);
         f2np = sqrt(acc);
         int crit1 = iteration > 0 && dynp <= C->c * cfg->delta_tolerance + DBL_EPS;
-        int crit2 = (S.Nobs + S.Nd == 0) || f2np <= cfg->delta_tolerance + DBL_EPS;
+        int crit2 = (S->Nobs + S->Nd == 0) || f2np <= cfg->delta_tolerance + DBL_EPS;
         int crit3 = C->akkt_tol <= cfg->tolerance + DBL_EPS;
         if (crit1 && crit2 && crit3) { done = 1; break; }
         int stall;
@@ -763,7 +818,7 @@ int nmpc_oracle_solve(const nmpc_config* cfg, const double* p, double* u, double
         else {
             int ca = dynp <= cfg->sufficient_decrease_coeff * dyn + DBL_EPS;
             int cp = f2np <= cfg->sufficient_decrease_coeff * f2n + DBL_EPS;
-            stall = (S.Nobs + S.Nd > 0) ? (ca && cp) : ca;
+            stall = (S->Nobs + S->Nd > 0) ? (ca && cp) : ca;
         }
         if (!stall) C->c *= cfg->penalty_update_factor;
         C->akkt_tol = fmax(C->akkt_tol * cfg->inner_tolerance_update, cfg->tolerance);
@@ -776,24 +831,33 @@ int nmpc_oracle_solve(const nmpc_config* cfg, const double* p, double* u, double
         st->exit_status = status; st->outer_iterations = num_outer; st->inner_iterations = inner_total;
         st->last_norm_fpr = C->norm_fpr; st->delta_y_norm_over_c = dynp / C->c; st->f2_norm = f2np;
         st->penalty = C->c;
-        st->cost = (status == NMPC_NOT_FINITE) ? NAN : eval_psi(&S, u, 0.0, 0, 0, 0, 0);
-        if (status != NMPC_NOT_FINITE) S.n_cost--;
-        st->n_cost_evals = S.n_cost; st->n_grad_evals = S.n_grad; st->reserved = 0;
+        st->cost = (status == NMPC_NOT_FINITE) ? NAN : eval_psi(S, u, 0.0, 0, 0, 0, 0);
+        if (status != NMPC_NOT_FINITE) S->n_cost--;
+        st->n_cost_evals = S->n_cost; st->n_grad_evals = S->n_grad; st->reserved = 0;
     }
-    free(F2); free(C); unstage(&S);
     return status;
+}
+
+int nmpc_oracle_solve(const nmpc_config* cfg, const double* p, double* u, double* y, nmpc_stats* st) {
+    workspace* W = ws_new();
+    if (!W) return -3;
+    int rc = solve_ws(W, cfg, p, u, y, st);
+    ws_free(W);
+    return rc;
 }
 
 int nmpc_oracle_eval(const nmpc_config* cfg, const double* p, const double* u, double c, const double* y,
                      double* psi, double* grad, double* F1, double* F2) {
-    staged S;
-    int rc = stage(&S, cfg, p);
-    if (rc) return -rc;
-    double gtmp[2 * MAXT];
-    double v = eval_psi(&S, u, c, y, grad ? grad : gtmp, F1, F2);
-    if (psi) *psi = v;
-    unstage(&S);
-    return 0;
+    workspace* W = ws_new();
+    if (!W) return -3;
+    int rc = stage(&W->S, cfg, p);
+    if (!rc) {
+        double gtmp[2 * MAXT];
+        double v = eval_psi(&W->S, u, c, y, grad ? grad : gtmp, F1, F2);
+        if (psi) *psi = v;
+    }
+    ws_free(W);
+    return rc ? -rc : 0;
 }
 
 /* batch drivers: one problem per OpenMP thread (nthreads <= 0: all cores) */
@@ -801,16 +865,25 @@ int nmpc_oracle_solve_batch(const nmpc_config* cfg, int32_t B, const double* Pm,
                             int32_t* status, nmpc_stats* stats, int nthreads) {
     const int np = nmpc_param_len(cfg), n2 = 2 * cfg->N_hor;
     int bad = 0;
+    g_trace = getenv("NMPC_ORACLE_TRACE") != NULL;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel
 #endif
-    for (int32_t b = 0; b < B; b++) {
-        nmpc_stats st;
-        int s = nmpc_oracle_solve(cfg, Pm + (size_t)b * np, U + (size_t)b * n2, Y ? Y + (size_t)b * n2 : 0, &st);
-        if (s < 0) bad = 1;
-        if (status) status[b] = s;
-        if (stats) stats[b] = st;
+    {
+        workspace* W = ws_new();
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+        for (int32_t b = 0; b < B; b++) {
+            nmpc_stats st;
+            memset(&st, 0, sizeof(st));
+            int s = W ? solve_ws(W, cfg, Pm + (size_t)b * np, U + (size_t)b * n2, Y ? Y + (size_t)b * n2 : 0, &st) : -3;
+            if (s < 0) bad = 1;
+            if (status) status[b] = s;
+            if (stats) stats[b] = st;
+        }
+        ws_free(W);
     }
     (void)nthreads;
     return bad ? NMPC_ERR_INVALID : NMPC_OK;
@@ -833,6 +906,14 @@ int nmpc_oracle_max_threads(void) {
     return omp_get_max_threads();
 #else
     return 1;
+#endif
+}
+
+int nmpc_oracle_is_serial(void) {
+#ifdef NMPC_ORACLE_SERIAL
+    return 1;
+#else
+    return 0;
 #endif
 }
 

@@ -11,6 +11,13 @@ in the build container.  Run:  python tests/golden/make_fixtures.py
       the CPU oracle (no GPU in this container).  Records every parameter vector the
       reference assembled (src/path_generator.py:378-379), every reply, the resulting
       trajectory and the A* path / obstacle vertices.
+  tests/golden/ref_runs.npz
+      the reference's own benchmark and demo runs, recorded the same way: maps 1-11 with
+      configs/default.yaml (src/gen_runtime_plots.py:21-33) and map 12 with sinus_object=True
+      (src/main.py:11-23: moving ellipses, ring update src/path_generator.py:306-316).  Every
+      STRIDE-th solver call of each run is kept as a self-contained tuple (p, warm start u/y the
+      server held, reply u, multipliers y, status, iteration counts) so that a test can replay all of
+      them as ONE batch.
   tests/golden/reference_helpers.npz
       outputs of the reference's pure helpers (rough_ref, get_brake_vel_ref) and of its
       PathPreProcessor (on top of our planner substitute) for maps 1, 3, 11, 12.
@@ -46,7 +53,8 @@ class OracleManager:
                                               if not k.startswith("reserved")})
         self.u = np.zeros((1, 2 * self.cfg.N_hor))
         self.y = np.zeros((1, 2 * self.cfg.N_hor))
-        OracleManager.log = {"P": [], "U": [], "status": [], "inner": [], "outer": []}
+        OracleManager.log = {"P": [], "U": [], "status": [], "inner": [], "outer": [], "U0": [], "Y0": [], "Y": [],
+                             "n_grad": [], "n_cost": []}
 
     def start(self):
         pass
@@ -62,10 +70,12 @@ class OracleManager:
         t0 = time.time()
         U, Y, st, stats = oracle_c.solve_batch(self.cfg, P, self.u, self.y, nthreads=1)
         ms = 1e3 * (time.time() - t0)
-        self.u, self.y = U, Y
         lg = OracleManager.log
-        lg["P"].append(P[0]); lg["U"].append(U[0].copy()); lg["status"].append(int(st[0]))
+        lg["U0"].append(self.u[0].copy()); lg["Y0"].append(self.y[0].copy())
+        self.u, self.y = U, Y
+        lg["P"].append(P[0]); lg["U"].append(U[0].copy()); lg["Y"].append(Y[0].copy()); lg["status"].append(int(st[0]))
         lg["inner"].append(int(stats["inner_iterations"][0])); lg["outer"].append(int(stats["outer_iterations"][0]))
+        lg["n_grad"].append(int(stats["n_grad_evals"][0])); lg["n_cost"].append(int(stats["n_cost_evals"][0]))
         return opengen_compat.SolverResponse(opengen_compat.SolverStatus(U[0], st[0], stats[0], ms), True)
 
 
@@ -126,6 +136,47 @@ def main():
                         xx=np.array(xx), xy=np.array(xy), uv=np.array(uv), uomega=np.array(uomega),
                         path=np.array(pg.ppp.path), vertices=np.array(pg.ppp.vert).reshape(-1, 2),
                         start=np.array(g.start), end=np.array(g.end))
+
+
+    record_runs(config, graphs, PathGenerator)
+
+
+STRIDE = 3   # every STRIDE-th solver call of a run is kept (plus the first and the last)
+
+
+def record_runs(config, graphs, PathGenerator):
+    """The reference's benchmark script (maps 1-11) and demo (map 12, sinus_object=True) through the
+    UNMODIFIED PathGenerator.run with the oracle-backed manager."""
+    out = {k: [] for k in ("P", "U0", "Y0", "U", "Y", "status", "inner", "outer", "n_grad", "n_cost", "map", "step")}
+    summary = []
+    for cx in range(1, 13):
+        g = graphs.get_graph(cx)
+        pg = PathGenerator(config, build=False, sinus_object=(cx == 12))
+        t0 = time.time()
+        xx, xy, uv, uomega, solver_times, overhead = pg.run(g, list(g.start), list(g.end))
+        lg = OracleManager.log
+        K = len(lg["P"])
+        # (a run that never reaches its goal — map 2 stalls in a local minimum facing away from its path — lasts the
+        #  reference's full 2500 steps: beyond step 300 only every 50th call is kept)
+        keep = sorted(set(range(0, min(K, 300), STRIDE)) | set(range(300, K, 50)) | {K - 1})
+        for k in keep:
+            for key in ("P", "U0", "Y0", "U", "Y", "status", "inner", "outer", "n_grad", "n_cost"):
+                out[key].append(lg[key][k])
+            out["map"].append(cx); out["step"].append(k)
+        P = np.array(lg["P"])
+        N, Nobs, Nd = config.N_hor, config.Nobs, config.Ndynobs
+        circ = P[:, 20 + N:20 + N + 3 * Nobs].reshape(K, Nobs, 3)
+        ell = P[:, 20 + N + 3 * Nobs:20 + N + 3 * Nobs + 5 * Nd * N].reshape(K, Nd, N, 5)
+        moving = bool(np.any(ell[:, :, :, 0] != 0.0))
+        summary.append((cx, K, len(keep), np.bincount(lg["status"], minlength=4).tolist(), int(np.max((circ[:, :, 2] != 0).sum(axis=1))),
+                        len(pg.ppp.vert), moving, float(xx[-1]), float(xy[-1])))
+        print(f"map {cx}: {K} steps ({len(keep)} kept) in {time.time() - t0:.0f}s, status counts {summary[-1][3]}, "
+              f"<= {summary[-1][4]} circles per step of {summary[-1][5]} corner vertices, moving ellipses: {moving}, "
+              f"final pose ({xx[-1]:.2f}, {xy[-1]:.2f}) goal ({g.end[0]}, {g.end[1]})")
+    np.savez_compressed(os.path.join(HERE, "ref_runs.npz"),
+                        **{k: np.array(v, dtype=(np.int32 if k in ("status", "inner", "outer", "n_grad", "n_cost", "map", "step") else np.float64))
+                           for k, v in out.items()},
+                        summary=np.array([[s[0], s[1], s[2], s[4], s[5], int(s[6])] for s in summary], dtype=np.int32))
 
 
 if __name__ == "__main__":

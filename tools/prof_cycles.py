@@ -15,8 +15,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import variants  # noqa: E402
 
-PHASES = ["OUTER_BEGIN", "INIT_A", "INIT_B", "STEP_BEGIN", "LIP", "COST_U", "LIP_LOOP", "LIP_RETRY", "IT0", "LS",
-          "STEP_DONE", "SOLVE_END", "F2", "FINAL", "EXIT", "HELP_WAIT", "HELP_EVAL"]
+PHASES = ["OUTER_BEGIN", "INIT", "STEP_BEGIN", "A", "RETRY", "LS", "STEP_DONE", "SOLVE_END", "F2", "EXIT"]
 SECT = ["theta_scan_sincos", "xy_scan", "cte", "obstacles", "cost_butterfly", "adjoint"]
 
 
@@ -45,16 +44,16 @@ def main():
         _, _, st1, stats1 = s.solve_batch(P2[b:b + 1])
         d = dbg.cpu().numpy()
         it = int(stats1["inner_iterations"][0])
-        ng, nc = int(d[1]), int(d[3])
+        ng, nc = int(d[1]), 0   # every call of eval() computes psi and grad psi at one point per group
         out = {"problem": int(b), "inner_iterations": it, "cycles_per_iteration": round(d[6] / max(it, 1)),
-               "grad_evals": ng, "cycles_per_grad_eval": round(d[0] / max(ng, 1)),
+               "eval_calls": ng, "cycles_per_eval_call": round(d[0] / max(ng, 1)),
                "cost_evals": nc, "cycles_per_cost_eval": round(d[2] / max(nc, 1)),
                "lbfgs_calls": int(d[5]), "cycles_per_lbfgs": round(d[4] / max(int(d[5]), 1)),
                "eval_share": round(float(d[0] + d[2]) / d[6], 3), "lbfgs_share": round(float(d[4]) / d[6], 3),
                "sections_cycles_per_eval": {k: round(d[8 + i] / max(ng + nc, 1)) for i, k in enumerate(SECT)},
                "kernel_ms": s.last_kernel_ms,
-               "phase_pre_cycles_per_iteration": {PHASES[i]: round(d[16 + i] / max(it, 1)) for i in range(16) if d[16 + i]},
-               "phase_post_cycles_per_iteration": {PHASES[i]: round(d[32 + i] / max(it, 1)) for i in range(16) if d[32 + i]}}
+               "phase_pre_cycles_per_iteration": {PHASES[i]: round(d[16 + i] / max(it, 1)) for i in range(len(PHASES)) if d[16 + i]},
+               "phase_post_cycles_per_iteration": {PHASES[i]: round(d[32 + i] / max(it, 1)) for i in range(len(PHASES)) if d[32 + i]}}
         print(json.dumps(out), flush=True)
     s.close()
 
