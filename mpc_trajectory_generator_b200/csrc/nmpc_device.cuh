@@ -73,7 +73,12 @@ enum { V_GRAD = 0, V_UHALF, V_FPR, V_DIR, V_GSTEP, V_OLDS, V_OLDG, V_U, V_YL, V_
 enum { H_X0 = 0, H_Y0, H_TH0, H_VINIT, H_WINIT, H_XREF, H_YREF, H_THREF, H_Q, H_QV, H_QTH, H_RV, H_RW, H_QN, H_QTHN,
        H_QCTE, H_AP, H_WP, H_INVTS,
        // warp-uniform solver state that is touched once per outer iteration (kept out of the registers)
-       H_F2N, H_DYN, H_F2NP, H_DYNP, H_NORMH, H_LIP, H_AKKT, H_NCIRC /* int */, H_COUNT = 28 };
+       H_F2N, H_DYN, H_F2NP, H_DYNP, H_NORMH, H_LIP, H_AKKT, H_NCIRC /* int */,
+       // PANOC scalars: every lane stores the same value and reads back its own store.  Keeping them (and the
+       // counters below) here instead of in registers is what lets the evaluation have the register file
+       H_GAMMA = 28, H_INVG, H_SIGMA, H_COST, H_NFPR, H_RHSLS, H_LBG, H_FBEU, H_IP, H_PENC, H_PINV, H_TBEG,
+       H_INTS = 40, H_COUNT = 48 };
+enum { I_NCOST = 0, I_NGRAD, I_ALM, I_INNER, I_NOUTER, I_STATUS, I_ISTATUS, I_ITLIP, I_NUMIT, I_FLAGS };
 #define SEG_STRIDE 6   // s1x s1y | dx dy | inv pad
 #define CIRC_STRIDE 4  // cx cy | r2 (original slot index as int in the 4th double)
 #define ELL_STRIDE 6   // ex ey | cosA sinA | 1/rx^2 1/ry^2
@@ -336,10 +341,20 @@ struct Warp {
     uint32_t sb;       // shared byte address of the arena
     uint32_t la;       // sb + 16*gl : this lane's element of slot row 0 inside vector 0
     uint32_t vstride;  // bytes per vector
-    uint32_t a_seg, a_circ, a_ell, a_ebd, a_rho, a_alpha, a_hdr, a_vref;
-    int lane, grp, gl, N, n_circ;  // n_circ: circles with r != 0 (zero-padded slots are skipped: they add exact zeros)
-    bool act[S];
-    int tix[S];
+    uint32_t a_hdr;
+    int o_seg, o_circ, o_ell, o_ebd, o_rho, o_alpha, o_vref;  // byte offsets inside the arena (the same for every warp)
+    int lane, grp, gl, N;
+    __device__ __forceinline__ uint32_t a_seg() const { return sb + o_seg; }
+    __device__ __forceinline__ uint32_t a_circ() const { return sb + o_circ; }
+    __device__ __forceinline__ uint32_t a_ell() const { return sb + o_ell; }
+    __device__ __forceinline__ uint32_t a_ebd() const { return sb + o_ebd; }
+    __device__ __forceinline__ uint32_t a_rho() const { return sb + o_rho; }
+    __device__ __forceinline__ uint32_t a_alpha() const { return sb + o_alpha; }
+    __device__ __forceinline__ uint32_t a_vref() const { return sb + o_vref; }
+    __device__ __forceinline__ int tix(int s) const { return S * gl + s; }
+    __device__ __forceinline__ bool act(int s) const { return S * gl + s < N; }
+    // n_circ: circles with r != 0 (zero-padded slots are skipped: they add exact zeros)
+    __device__ __forceinline__ int n_circ() const { return ldsi(a_hdr + 8u * H_NCIRC); }
 #ifdef NMPC_PROFILE
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // cycles per eval section (tools/prof_cycles.py)
 #endif
@@ -351,14 +366,9 @@ struct Warp {
         sb = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)warp * (uint32_t)L.total * 8u;
         la = sb + 16u * gl;
         vstride = (uint32_t)L.vlen * 8u;
-        a_seg = sb + L.seg * 8u; a_circ = sb + L.circ * 8u; a_ell = sb + L.ell * 8u; a_ebd = sb + L.ebd * 8u; a_rho = sb + L.rho * 8u;
-        a_alpha = sb + L.alpha * 8u; a_hdr = sb + L.hdr * 8u; a_vref = sb + L.vref * 8u;
-        n_circ = 0;
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            tix[s] = S * gl + s;
-            act[s] = tix[s] < N;
-        }
+        o_seg = L.seg * 8; o_circ = L.circ * 8; o_ell = L.ell * 8; o_ebd = L.ebd * 8; o_rho = L.rho * 8;
+        o_alpha = L.alpha * 8; o_vref = L.vref * 8;
+        a_hdr = sb + L.hdr * 8u;
     }
     __device__ __forceinline__ double hdr(int i) const { return lds1(a_hdr + 8u * i); }
     // vector k of the arena: every lane reads its S (v, w) pairs; all groups see the same vector
@@ -381,7 +391,7 @@ struct Warp {
         if (lane < 8) sts1(a_hdr + 8u * lane, p[lane]);
         if (lane >= 8 && lane < 18) sts1(a_hdr + 8u * lane, p[lane + 2]);
         if (lane == 18) sts1(a_hdr + 8u * H_INVTS, 1.0 / cfg.ts);
-        for (int t = lane; t < G * S; t += 32) sts1(a_vref + 8u * t, t < N ? p[NMPC_NZ + t] : 0.0);
+        for (int t = lane; t < G * S; t += 32) sts1(a_vref() + 8u * t, t < N ? p[NMPC_NZ + t] : 0.0);
         const double* pc = p + NMPC_NZ + N;
         int nreal = 0;
         for (int k0 = 0; k0 < Nobs; k0 += 32) {  // order-preserving compaction of the non-padded circles
@@ -396,7 +406,7 @@ struct Warp {
             const unsigned m = __ballot_sync(FULL, real);
             if (real) {
                 const int pos = nreal + __popc(m & ((1u << lane) - 1u));
-                const uint32_t a = a_circ + 32u * pos;
+                const uint32_t a = a_circ() + 32u * pos;
                 sts2(a, make_double2(cx, cy));
                 sts1(a + 16u, r * r);
                 stsi(a + 24u, k);
@@ -404,12 +414,11 @@ struct Warp {
             nreal += __popc(m);
         }
         if (lane < 4) {  // the circle loop reads four at a time: dummies that can never be entered (r^2 = -1)
-            const uint32_t a = a_circ + 32u * (nreal + lane);
+            const uint32_t a = a_circ() + 32u * (nreal + lane);
             sts2(a, make_double2(0.0, 0.0));
             sts1(a + 16u, -1.0);
             stsi(a + 24u, 0);
         }
-        n_circ = nreal;
         if (lane == 0) stsi(a_hdr + 8u * H_NCIRC, nreal);
         const double* pe = pc + 3 * Nobs;
         const int ne = Nd * N;
@@ -417,7 +426,7 @@ struct Warp {
             const double* e = pe + 5 * i;  // obstacle-major then time: offset k*5N + 5t = 5*(k*N + t)
             double sa, ca;
             nm_sincos(e[4], sa, ca);
-            const uint32_t a = a_ell + 48u * i;
+            const uint32_t a = a_ell() + 48u * i;
             sts2(a, make_double2(e[0], e[1]));
             sts2(a + 16u, make_double2(ca, sa));
             sts2(a + 32u, make_double2(1.0 / (e[2] * e[2]), 1.0 / (e[3] * e[3])));
@@ -443,7 +452,7 @@ struct Warp {
                 R = fmax(R, r);
             }
             R = R * (1.0 + 1e-6) + 1e-9;
-            const uint32_t a = a_ebd + 32u * k;
+            const uint32_t a = a_ebd() + 32u * k;
             sts2(a, make_double2(bx, by));
             sts1(a + 16u, bad ? CUDART_NAN : R * R);
         }
@@ -454,7 +463,7 @@ struct Warp {
                 const int i = (ii < N) ? ii : N - 1;
                 double ax = pr[3 * (i - 1)], ay = pr[3 * (i - 1) + 1];
                 double dx = pr[3 * i] - ax, dy = pr[3 * i + 1] - ay;
-                const uint32_t a = a_seg + 48u * ii;
+                const uint32_t a = a_seg() + 48u * ii;
                 sts2(a, make_double2(ax, ay));
                 sts2(a + 16u, make_double2(dx, dy));
                 sts1(a + 32u, 1.0 / (fma(dx, dx, dy * dy) + 1e-16));
@@ -475,7 +484,9 @@ struct Warp {
 
     // psi, grad psi and |F2|^2 of the staged problem at this GROUP's point uv (every group evaluates its own
     // point with its own penalty parameter; the multipliers come from the arena vector V_YL)
-    __device__ double eval(const double2 (&uv)[S], const Pen pn, double2 (&gout)[S], double& pen_out,
+    // The penalty parameter c comes from the arena header (H_PENC, H_PINV = 1 / max(c, 1)); zero_c: this lane's
+    // group evaluates with c = 0 (f(u) alone).
+    __device__ double eval(const double2 (&uv)[S], const bool zero_c, double2 (&gout)[S], double& pen_out,
                            double* __restrict__ F2g) {
         const double ts = cfg.ts;
         PROF_BEGIN();
@@ -483,7 +494,7 @@ struct Warp {
         double cth[S];
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            const double v = act[s] ? ts * uv[s].y : 0.0;
+            const double v = act(s) ? ts * uv[s].y : 0.0;
             cth[s] = (s == 0) ? v : cth[s - 1] + v;
         }
         const double Eth = gscan_up_excl<G>(cth[S - 1], gl);
@@ -500,8 +511,8 @@ struct Warp {
             double ca[S], cb[S];
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                const double va = act[s] ? ts * (uv[s].x * cs[s]) : 0.0;
-                const double vb = act[s] ? ts * (uv[s].x * sn[s]) : 0.0;
+                const double va = act(s) ? ts * (uv[s].x * cs[s]) : 0.0;
+                const double vb = act(s) ? ts * (uv[s].x * sn[s]) : 0.0;
                 ca[s] = (s == 0) ? va : ca[s - 1] + va;
                 cb[s] = (s == 0) ? vb : cb[s - 1] + vb;
             }
@@ -562,7 +573,7 @@ struct Warp {
             // two half-trips per trip, each working on segments fetched one half-trip earlier (no moves, the loads
             // of the next half-trip are in flight behind the arithmetic of this one)
             Seg ga, gb;
-            uint32_t as = a_seg + 48u;
+            uint32_t as = a_seg() + 48u;
             ldseg(as, ga);
 #pragma unroll 1
             for (int i = 1; i < N; i += 2 * U, as += 96u * U) {
@@ -574,7 +585,7 @@ struct Warp {
 #pragma unroll
             for (int s = 0; s < S; s++) {  // redo the arg-min segment (same operations, same bits) for the gradient
                 mind2[s] = best[s];
-                const uint32_t ab = a_seg + 48u * bi[s];
+                const uint32_t ab = a_seg() + 48u * bi[s];
                 const double2 s1 = lds2(ab), d = lds2(ab + 16u);
                 const double inv = lds1(ab + 32u);
                 const double px = X[s] - s1.x, py = Y[s] - s1.y;
@@ -597,11 +608,12 @@ struct Warp {
             // pass 1: the inside-tests of all circles back to back (no votes, no branches: the chains overlap); every
             // lane notes the circles one of its points is inside of, one warp-wide OR gives the circles that need
             // pass 2 (group sum, penalty, gradient) — rarely any.  32 circles per round.
+            const int ncirc = n_circ();
 #pragma unroll 1
-            for (int kb = 0; kb < n_circ; kb += 32) {
-                const int kn = min(32, n_circ - kb);
+            for (int kb = 0; kb < ncirc; kb += 32) {
+                const int kn = min(32, ncirc - kb);
                 unsigned mine = 0;
-                uint32_t ac = a_circ + 32u * kb;
+                uint32_t ac = a_circ() + 32u * kb;
 #pragma unroll 1
                 for (int k = 0; k < kn; k += 4, ac += 128u) {
 #pragma unroll
@@ -612,7 +624,7 @@ struct Warp {
 #pragma unroll
                         for (int s = 0; s < S; s++) {
                             const double dx = X[s] - cxy.x, dy = Y[s] - cxy.y;
-                            in = in || (act[s] && fma(-dy, dy, fma(-dx, dx, r2)) > 0.0);
+                            in = in || (act(s) && fma(-dy, dy, fma(-dx, dx, r2)) > 0.0);
                         }
                         mine |= in ? (1u << (k + q)) : 0u;
                     }
@@ -621,7 +633,7 @@ struct Warp {
                 while (todo) {
                     const int k = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    const uint32_t a1 = a_circ + 32u * (kb + k);
+                    const uint32_t a1 = a_circ() + 32u * (kb + k);
                     const double2 cxy = lds2(a1);
                     const double r2 = lds1(a1 + 16u);
                     double hp[S], dx[S], dy[S];
@@ -630,7 +642,7 @@ struct Warp {
                         dx[s] = X[s] - cxy.x;
                         dy[s] = Y[s] - cxy.y;
                         const double hh = fma(-dy[s], dy[s], fma(-dx[s], dx[s], r2));
-                        hp[s] = (act[s] && hh > 0.0) ? hh : 0.0;
+                        hp[s] = (act(s) && hh > 0.0) ? hh : 0.0;
                     }
                     double g = hp[0];
 #pragma unroll
@@ -638,7 +650,7 @@ struct Warp {
                     g = gsum<G>(g);
                     if (F2g && lane == 0 && g > 0.0) F2g[ldsi(a1 + 24u)] = g;
                     pen = fma(g, g, pen);
-                    const double cg = pn.c * g;
+                    const double cg = (zero_c ? 0.0 : hdr(H_PENC)) * g;
 #pragma unroll
                     for (int s = 0; s < S; s++)
                         if (hp[s] > 0.0) {
@@ -651,13 +663,13 @@ struct Warp {
 #pragma unroll 1
             for (int k = 0; k < Nd; k++) {
                 {   // nobody inside the disc around all poses of this obstacle: it adds exact zeros
-                    const double2 bxy = lds2(a_ebd + 32u * k);
-                    const double R2 = lds1(a_ebd + 32u * k + 16u);
+                    const double2 bxy = lds2(a_ebd() + 32u * k);
+                    const double R2 = lds1(a_ebd() + 32u * k + 16u);
                     bool near = false;
 #pragma unroll
                     for (int s = 0; s < S; s++) {
                         const double dx = X[s] - bxy.x, dy = Y[s] - bxy.y;
-                        near = near || (act[s] && fma(dx, dx, dy * dy) < R2);
+                        near = near || (act(s) && fma(dx, dx, dy * dy) < R2);
                     }
                     if (!__any_sync(FULL, near)) continue;
                 }
@@ -665,7 +677,7 @@ struct Warp {
                 bool any = false;
 #pragma unroll
                 for (int s = 0; s < S; s++) {
-                    const uint32_t ae = a_ell + 48u * (k * N + (act[s] ? tix[s] : 0));
+                    const uint32_t ae = a_ell() + 48u * (k * N + (act(s) ? tix(s) : 0));
                     const double2 exy = lds2(ae), csa = lds2(ae + 16u), ir = lds2(ae + 32u);
                     const double dx = X[s] - exy.x, dy = Y[s] - exy.y;
                     eca[s] = csa.x;
@@ -673,7 +685,7 @@ struct Warp {
                     const double ea = fma(dx, csa.x, dy * csa.y);
                     const double eb = fma(dx, csa.y, -(dy * csa.x));
                     const double hh = fma(-(eb * eb), ir.y, fma(-(ea * ea), ir.x, 1.0));
-                    const bool in = act[s] && hh > 0.0;
+                    const bool in = act(s) && hh > 0.0;
                     hp[s] = in ? hh : 0.0;
                     any = any || in;
                     ta[s] = ea * ir.x;
@@ -686,7 +698,7 @@ struct Warp {
                     g = gsum<G>(g);
                     if (F2g && lane == 0 && g > 0.0) F2g[cfg.Nobs + k] = g;
                     pen = fma(g, g, pen);
-                    const double cg = pn.c * g;
+                    const double cg = (zero_c ? 0.0 : hdr(H_PENC)) * g;
 #pragma unroll
                     for (int s = 0; s < S; s++)
                         if (hp[s] > 0.0) {
@@ -700,6 +712,10 @@ struct Warp {
         }
         pen_out = pen;
         PROF_MARK(3);
+        Pen pn;
+        pn.c = zero_c ? 0.0 : hdr(H_PENC);
+        pn.hc = 0.5 * pn.c;
+        pn.inv_c = zero_c ? 1.0 : hdr(H_PINV);
 
         // ---- stage cost (:84-86), acceleration cost and ALM term (:157-171)
         const double inv_ts = hdr(H_INVTS);
@@ -717,7 +733,7 @@ struct Warp {
                 const double2 yl = lds2(la + V_YL * vstride + 16u * G * s);
                 double c0 = w_rv * (v * v);
                 c0 = fma(w_rw, w * w, c0);
-                vref[s] = lds1(a_vref + 8u * tix[s]);
+                vref[s] = lds1(a_vref() + 8u * tix(s));
                 const double dv = v - vref[s];
                 c0 = fma(w_qv, dv * dv, c0);
                 const double ex = ((s == 0) ? xp0 : X[s > 0 ? s - 1 : 0]) - xref, ey = ((s == 0) ? yp0 : Y[s > 0 ? s - 1 : 0]) - yref;
@@ -732,9 +748,9 @@ struct Warp {
                 const double da = sel_excess(za, cfg.lin_acc_min, cfg.lin_acc_max);
                 const double dw = sel_excess(zw, -cfg.ang_acc_max, cfg.ang_acc_max);
                 c0 = fma(pn.hc, fma(da, da, dw * dw), c0);
-                cl[s] = act[s] ? c0 : 0.0;
-                Aa[s] = act[s] ? fma(pn.c, da, (2.0 * w_ap) * acc) * inv_ts : 0.0;
-                Aw[s] = act[s] ? fma(pn.c, dw, (2.0 * w_wp) * aac) * inv_ts : 0.0;
+                cl[s] = act(s) ? c0 : 0.0;
+                Aa[s] = act(s) ? fma(pn.c, da, (2.0 * w_ap) * acc) * inv_ts : 0.0;
+                Aw[s] = act(s) ? fma(pn.c, dw, (2.0 * w_wp) * aac) * inv_ts : 0.0;
             }
         }
         // terminal cost at t = N-1 (:148)
@@ -757,11 +773,11 @@ struct Warp {
         double mth[S];
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            const bool last = !(tix[s] + 1 < N);
+            const bool last = !(tix(s) + 1 < N);
             const double qq = last ? w_qN : w_q, qt = last ? w_qthN : w_qth;
-            gX[s] = act[s] ? fma(2.0 * qq, X[s] - xref, gX[s]) : 0.0;
-            gY[s] = act[s] ? fma(2.0 * qq, Y[s] - yref, gY[s]) : 0.0;
-            mth[s] = act[s] ? (2.0 * qt) * (TH[s] - thref) : 0.0;
+            gX[s] = act(s) ? fma(2.0 * qq, X[s] - xref, gX[s]) : 0.0;
+            gY[s] = act(s) ? fma(2.0 * qq, Y[s] - yref, gY[s]) : 0.0;
+            mth[s] = act(s) ? (2.0 * qt) * (TH[s] - thref) : 0.0;
         }
         double LX[S], LY[S], csum = cl[0];
 #pragma unroll
@@ -785,7 +801,7 @@ struct Warp {
         PROF_MARK(4);
         double nn[S], TT[S];
 #pragma unroll
-        for (int s = 0; s < S; s++) nn[s] = act[s] ? (ts * uv[s].x) * fma(cs[s], LY[s], -(sn[s] * LX[s])) : 0.0;
+        for (int s = 0; s < S; s++) nn[s] = act(s) ? (ts * uv[s].x) * fma(cs[s], LY[s], -(sn[s] * LX[s])) : 0.0;
         {
             double nnx = __shfl_down_sync(FULL, nn[0], 1, G);  // the next lane's first step
             if (gl == G - 1) nnx = 0.0;
@@ -793,7 +809,7 @@ struct Warp {
 #pragma unroll
             for (int s = S - 1; s >= 0; s--) {
                 const double nx = (s == S - 1) ? nnx : nn[s < S - 1 ? s + 1 : s];
-                const double rr = act[s] ? mth[s] + nx : 0.0;
+                const double rr = act(s) ? mth[s] + nx : 0.0;
                 dT[s] = (s == S - 1) ? rr : dT[s < S - 1 ? s + 1 : s] + rr;
             }
             const double ET = gscan_down_excl<G>(dT[0], gl);
@@ -814,7 +830,7 @@ struct Warp {
                 const double lw = (2.0 * w_rw) * w + (Aw[s] - Wn);
                 const double gv = fma(ts, fma(cs[s], LX[s], sn[s] * LY[s]), lv);
                 const double gw = fma(ts, TT[s], lw);
-                gout[s] = act[s] ? make_double2(gv, gw) : make_double2(0.0, 0.0);
+                gout[s] = act(s) ? make_double2(gv, gw) : make_double2(0.0, 0.0);
             }
         }
         PROF_MARK(5);
@@ -833,8 +849,11 @@ __device__ __forceinline__ unsigned long long nm_globaltimer() {
     return t;
 }
 
+// Solves the staged problem.  The decision vector lives in the arena (V_U: start point in, solution out) and the
+// multipliers in V_YL; the warp-uniform solver state lives in the arena header (H_GAMMA ..., I_*), so that across an
+// evaluation only a handful of registers stay live.
 template <int G, int S>
-__device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out, long long* prof_out = nullptr) {
+__device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_out = nullptr) {
     constexpr int NG = 32 / G;
 #ifdef NMPC_PROFILE
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -843,47 +862,53 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
     const nmpc_config& cfg = W.cfg;
     const int lane = W.lane, grp = W.grp;
     const int mem = cfg.lbfgs_memory, mem1 = cfg.lbfgs_memory + 1;
-    const int nf2 = cfg.Nobs + cfg.Ndynobs;
-    // warp-uniform state
-    double gamma = 0.0, inv_gamma = 0.0, sigma = 0.0, cost = 0.0, norm_fpr = 0.0;
-    double rhs_ls = 0.0, lb_gamma = 1.0, fbe_u = 0.0, ip = 0.0;
-    // rarely touched warp-uniform scalars live in the arena header: every lane stores the same value and
-    // reads back its own store, so no synchronisation is involved
+    // warp-uniform state in the arena header: every lane stores the same value and reads back its own store
     auto sget = [&](int i) { return lds1(W.a_hdr + 8u * i); };
     auto sput = [&](int i, double v) { sts1(W.a_hdr + 8u * i, v); };
+    auto iget = [&](int i) { return ldsi(W.a_hdr + 8u * H_INTS + 4u * i); };
+    auto iput = [&](int i, int v) { stsi(W.a_hdr + 8u * H_INTS + 4u * i, v); };
     sput(H_AKKT, cfg.initial_tolerance);
     sput(H_F2N, 0.0);
     sput(H_DYN, 0.0);
     sput(H_F2NP, 0.0);
     sput(H_DYNP, 0.0);
     sput(H_LIP, 0.0);
-    Pen pn = make_pen(cfg.initial_penalty);
-    int iteration = 0, n_cost = 0, n_grad = 0, lb_active = 0, lb_first = 1, lb_head = 0;
-    int alm_iter = 0, inner_total = 0, num_outer = 0, status = NMPC_CONVERGED, inner_status = NMPC_CONVERGED;
-    int num_iter = 0, it_lip = 0, e0 = 0, gfirst = 0;
-    bool cont = true, fbe_valid = false, timed_out = false;
-    const double inv_ts = W.hdr(H_INVTS);
-    const unsigned long long t_begin = cfg.max_duration_micros > 0 ? nm_globaltimer() : 0ull;
-    const unsigned long long t_budget = (unsigned long long)(cfg.max_duration_micros > 0 ? cfg.max_duration_micros : 0) * 1000ull;
+    sput(H_NFPR, 0.0);
+    sput(H_PENC, cfg.initial_penalty);
+    sput(H_PINV, 1.0 / fmax(cfg.initial_penalty, 1.0));
+    iput(I_NCOST, 0); iput(I_NGRAD, 0); iput(I_ALM, 0); iput(I_INNER, 0); iput(I_NOUTER, 0);
+    iput(I_STATUS, NMPC_CONVERGED); iput(I_ISTATUS, NMPC_CONVERGED); iput(I_ITLIP, 0); iput(I_NUMIT, 0);
+    // the few values that stay in registers
+    int iteration = 0, lb_active = 0, lb_head = 0, e0 = 0;
+    // flags: 1 lb_first, 2 gfirst (group 0 of the current call evaluates u_half), 4 cont, 8 fbe_valid, 16 timed_out
+    enum { F_LBFIRST = 1, F_GFIRST = 2, F_CONT = 4, F_FBE = 8, F_TIMEOUT = 16 };
+    int flags = F_LBFIRST | F_CONT;
+    if (cfg.max_duration_micros > 0) sput(H_TBEG, __longlong_as_double((long long)nm_globaltimer()));
+    auto out_of_time = [&]() -> bool {
+        if (cfg.max_duration_micros <= 0) return false;
+        const unsigned long long t0 = (unsigned long long)__double_as_longlong(sget(H_TBEG));
+        return nm_globaltimer() - t0 > (unsigned long long)cfg.max_duration_micros * 1000ull;
+    };
 
     double2 x[S], g[S];  // this group's evaluation point / gradient out
     double pen = 0.0;
-    Pen pn_eval = pn;
+    bool zero_c = false;
     int phase = PH_OUTER_BEGIN;
 
     auto set_gamma = [&](double gm) {  // sigma only changes with gamma: computed here, not once per iteration
-        gamma = gm;
-        inv_gamma = 1.0 / gm;
-        sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * gm);
+        sput(H_GAMMA, gm);
+        sput(H_INVG, 1.0 / gm);
+        sput(H_SIGMA, (1.0 - GAMMA_L_COEFF) / (4.0 * gm));
     };
     // gradient_step() + half_step(): gs = p - gamma*grad ; uh = Proj_U(gs)
     auto grad_step_half = [&](const double2(&p)[S], const double2(&gr)[S], double2(&gs)[S], double2(&uh)[S]) {
+        const double gamma = sget(H_GAMMA);
 #pragma unroll
         for (int s = 0; s < S; s++) {
             gs[s].x = fma(-gamma, gr[s].x, p[s].x);
             gs[s].y = fma(-gamma, gr[s].y, p[s].y);
-            uh[s].x = W.act[s] ? clampd(gs[s].x, cfg.lin_vel_min, cfg.lin_vel_max) : 0.0;
-            uh[s].y = W.act[s] ? clampd(gs[s].y, -cfg.ang_vel_max, cfg.ang_vel_max) : 0.0;
+            uh[s].x = W.act(s) ? clampd(gs[s].x, cfg.lin_vel_min, cfg.lin_vel_max) : 0.0;
+            uh[s].y = W.act(s) ? clampd(gs[s].y, -cfg.ang_vel_max, cfg.ang_vel_max) : 0.0;
         }
     };
     // per-lane partials (serial over the lane's steps), then the group sum
@@ -903,28 +928,28 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
         }
         return e;
     };
-    auto compute_fpr = [&](const double2(&uh)[S], double2(&fpr)[S]) {
+    // fpr = u - u_half and its norm (returned; also kept in the header)
+    auto compute_fpr = [&](const double2(&u)[S], const double2(&uh)[S], double2(&fpr)[S]) -> double {
 #pragma unroll
         for (int s = 0; s < S; s++) fpr[s] = make_double2(u[s].x - uh[s].x, u[s].y - uh[s].y);
-        norm_fpr = sqrt(gsum<G>(dot(fpr, fpr)));
-    };
-    auto slot = [&](int i) {
-        int sl = lb_head + i;
-        return (sl >= mem1) ? sl - mem1 : sl;
+        const double nf = sqrt(gsum<G>(dot(fpr, fpr)));
+        sput(H_NFPR, nf);
+        return nf;
     };
     // Lipschitz test of PANOC's step size (update_lipschitz_constant): true = the step size must be halved
     auto lip_test_fails = [&](double cost_half) -> bool {
-        const double rhs = cost + LIPSCHITZ_UPDATE_EPSILON * fabs(cost) - ip + (GAMMA_L_COEFF * 0.5 * inv_gamma) * (norm_fpr * norm_fpr);
-        return cost_half > rhs && it_lip < MAX_LIPSCHITZ_UPDATE_ITERATIONS && sget(H_LIP) < MAX_LIPSCHITZ_CONSTANT;
+        const double cost = sget(H_COST), nf = sget(H_NFPR);
+        const double rhs = cost + LIPSCHITZ_UPDATE_EPSILON * fabs(cost) - sget(H_IP) + (GAMMA_L_COEFF * 0.5 * sget(H_INVG)) * (nf * nf);
+        return cost_half > rhs && iget(I_ITLIP) < MAX_LIPSCHITZ_UPDATE_ITERATIONS && sget(H_LIP) < MAX_LIPSCHITZ_CONSTANT;
     };
     // halve gamma, drop the L-BFGS memory, recompute the half step; every group then evaluates psi(u_half)
     auto lip_halve = [&]() {
         lb_active = 0;
-        lb_first = 1;
-        fbe_valid = false;
+        flags = (flags | F_LBFIRST) & ~F_FBE;
         sput(H_LIP, sget(H_LIP) * 2.0);
-        set_gamma(gamma / 2.0);
-        double2 gr[S], gs[S], uh[S];
+        set_gamma(sget(H_GAMMA) / 2.0);
+        double2 u[S], gr[S], gs[S], uh[S];
+        W.ld(V_U, u);
         W.ld(V_GRAD, gr);
         grad_step_half(u, gr, gs, uh);
         __syncwarp();
@@ -933,27 +958,28 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
         __syncwarp();
 #pragma unroll
         for (int s = 0; s < S; s++) x[s] = uh[s];
-        pn_eval = pn;
+        zero_c = false;
         phase = PH_RETRY;
     };
     // line-search trial points of a call whose groups hold the exponents e0 + grp - gfirst (tau = 2^-e, at most 2^-10)
-    auto form_trials = [&](const double2(&uh)[S]) {
+    auto form_trials = [&]() {
+        const int gfirst = (flags & F_GFIRST) ? 1 : 0;
         int e = e0 + grp - gfirst;
         e = e > MAX_LINESEARCH_ITERATIONS ? MAX_LINESEARCH_ITERATIONS : e;
         // tau = 2^-e exactly (the reference halves tau e times)
         const double tau = __longlong_as_double((long long)(1023 - (e < 0 ? 0 : e)) << 52);
         const double om = 1.0 - tau;
-        double2 fpr[S], dir[S];
+        double2 u[S], fpr[S], dir[S];
+        W.ld(V_U, u);
         W.ld(V_FPR, fpr);
         W.ld(V_DIR, dir);
-        const bool is_half = grp < gfirst;  // group 0 of a first call evaluates psi(u_half)
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            const double tx = fma(-tau, dir[s].x, fma(-om, fpr[s].x, u[s].x));
-            const double ty = fma(-tau, dir[s].y, fma(-om, fpr[s].y, u[s].y));
-            x[s] = is_half ? uh[s] : make_double2(tx, ty);
+            x[s].x = fma(-tau, dir[s].x, fma(-om, fpr[s].x, u[s].x));
+            x[s].y = fma(-tau, dir[s].y, fma(-om, fpr[s].y, u[s].y));
         }
-        pn_eval = pn;
+        if (grp < gfirst) W.ld(V_UHALF, x);  // group 0 of a first call evaluates psi(u_half)
+        zero_c = false;
     };
     // right-hand side of the line search from the forward-backward envelope at u (compute_rhs_ls)
     auto rhs_from_envelope = [&]() {
@@ -963,22 +989,25 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
         W.ld(V_GRAD, gr);
         double dist2 = diff2(gs, uh), gg = dot(gr, gr);
         gsum2<G>(dist2, gg);
-        const double fbe = cost - (0.5 * gamma) * gg + (0.5 * dist2) * inv_gamma;
-        rhs_ls = fbe - sigma * (norm_fpr * norm_fpr);
+        const double nf = sget(H_NFPR);
+        const double fbe = sget(H_COST) - (0.5 * sget(H_GAMMA)) * gg + (0.5 * dist2) * sget(H_INVG);
+        sput(H_RHSLS, fbe - sget(H_SIGMA) * (nf * nf));
     };
     // update_no_linesearch() of iteration 0: u <- u_half with the cost and gradient group 0 has just evaluated there
     auto first_iteration_update = [&](double cost_half) {
         W.st(V_GRAD, g);  // group 0 evaluated u_half
         __syncwarp();
-        double2 gr[S], gs[S], uh[S];
+        double2 u[S], gr[S], gs[S], uh[S];
         W.ld(V_UHALF, u);
         W.ld(V_GRAD, gr);
-        cost = cost_half;
+        sput(H_COST, cost_half);
         grad_step_half(u, gr, gs, uh);
+        __syncwarp();
+        W.st(V_U, u);
         W.st(V_GSTEP, gs);
         W.st(V_UHALF, uh);
         __syncwarp();
-        n_grad++;
+        iput(I_NGRAD, iget(I_NGRAD) + 1);
         iteration++;
         phase = PH_STEP_DONE;
     };
@@ -1003,12 +1032,12 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
         // ------------------------------------------------------------------ pre: pick this group's x
         switch (phase) {
             case PH_OUTER_BEGIN: {
-                if (t_budget && nm_globaltimer() - t_begin > t_budget) {  // AlmOptimizer::solve: no time left
-                    status = NMPC_NOT_CONVERGED_OUT_OF_TIME;
+                if (out_of_time()) {  // AlmOptimizer::solve: no time left
+                    iput(I_STATUS, NMPC_NOT_CONVERGED_OUT_OF_TIME);
                     phase = PH_EXIT;
                     continue;
                 }
-                num_outer++;
+                iput(I_NOUTER, iget(I_NOUTER) + 1);
                 {
                     double2 yl[S];
                     W.ld(V_YL, yl);
@@ -1023,16 +1052,17 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                 // panoc init: cost and gradient at u (group 0) and the gradient at u + h (the other groups) in one
                 // call; estimate_loc_lip leaves u perturbed by h
                 lb_active = 0;
-                lb_first = 1;
-                fbe_valid = false;
+                flags = (flags | F_LBFIRST) & ~F_FBE;
                 iteration = 0;
                 {
+                    double2 u[S];
+                    W.ld(V_U, u);
                     double e = 0.0;
 #pragma unroll
                     for (int s = 0; s < S; s++) {
                         const double ex_ = EPSILON_LIPSCHITZ * u[s].x, ey_ = EPSILON_LIPSCHITZ * u[s].y;
-                        const double hx = W.act[s] ? ((ex_ > DELTA_LIPSCHITZ) ? ex_ : DELTA_LIPSCHITZ) : 0.0;
-                        const double hy = W.act[s] ? ((ey_ > DELTA_LIPSCHITZ) ? ey_ : DELTA_LIPSCHITZ) : 0.0;
+                        const double hx = W.act(s) ? ((ex_ > DELTA_LIPSCHITZ) ? ex_ : DELTA_LIPSCHITZ) : 0.0;
+                        const double hy = W.act(s) ? ((ey_ > DELTA_LIPSCHITZ) ? ey_ : DELTA_LIPSCHITZ) : 0.0;
                         const double t = fma(hy, hy, hx * hx);
                         e = (s == 0) ? t : e + t;
                         const double2 up = make_double2(u[s].x + hx, u[s].y + hy);
@@ -1040,19 +1070,23 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                         u[s] = up;
                     }
                     sput(H_NORMH, sqrt(gsum<G>(e)));
+                    __syncwarp();
+                    W.st(V_U, u);
                 }
-                pn_eval = pn;
+                zero_c = false;
                 __syncwarp();
                 phase = PH_INIT;
                 break;
             }
             case PH_STEP_BEGIN: {
-                double2 gr[S], uh[S], fpr[S];
+                double2 u[S], gr[S], uh[S], fpr[S];
+                W.ld(V_U, u);
                 W.ld(V_GRAD, gr);
                 W.ld(V_UHALF, uh);
-                compute_fpr(uh, fpr);
+                const double norm_fpr = compute_fpr(u, uh, fpr);
                 bool exit_now = false;
-                if (norm_fpr < cfg.tolerance) {
+                if (__builtin_expect(norm_fpr < cfg.tolerance, 0)) {
+                    const double inv_gamma = sget(H_INVG);
                     double e = 0.0;
 #pragma unroll
                     for (int s = 0; s < S; s++) {
@@ -1070,15 +1104,15 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                 }
                 __syncwarp();
                 W.st(V_FPR, fpr);
-                it_lip = 0;
+                iput(I_ITLIP, 0);
                 // <grad, fpr> for the Lipschitz test and, when a previous (state, fpr) pair exists, the three
                 // inner products of the L-BFGS update (s.y, s.s, y.y) in ONE interleaved group sum.
                 // The update and the direction are computed BEFORE psi(u_half) is known: if the Lipschitz test then
                 // fails (rare), lip_halve() drops the memory exactly like the reference does before its update.
                 double2 q[S];
-                if (lb_first) {
-                    ip = gsum<G>(dot(gr, fpr));
-                    lb_first = 0;
+                if (flags & F_LBFIRST) {
+                    sput(H_IP, gsum<G>(dot(gr, fpr)));
+                    flags &= ~F_LBFIRST;
                     W.st(V_OLDS, u);
                     W.st(V_OLDG, fpr);
                 } else {
@@ -1090,11 +1124,12 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                         sv[s] = make_double2(u[s].x - os[s].x, u[s].y - os[s].y);
                         yv[s] = make_double2(fpr[s].x - og[s].x, fpr[s].y - og[s].y);
                     }
-                    double ys = dot(sv, yv), ss = dot(sv, sv), yy = dot(yv, yv);
-                    ip = dot(gr, fpr);
+                    double ys = dot(sv, yv), ss = dot(sv, sv), yy = dot(yv, yv), ip = dot(gr, fpr);
                     gsum4<G>(ip, ys, ss, yy);
+                    sput(H_IP, ip);
                     // lbfgs update_hessian(g = fpr, state = u)
-                    const int tmp = slot(mem);
+                    int tmp = lb_head + mem;
+                    tmp = (tmp >= mem1) ? tmp - mem1 : tmp;
                     W.st(V_S + tmp, sv);
                     W.st(V_Y + tmp, yv);
                     const double rho_new = 1.0 / ys;
@@ -1107,19 +1142,19 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                     if (accept) {
                         W.st(V_OLDS, u);
                         W.st(V_OLDG, fpr);
-                        sts1_if(W.a_rho + 8u * tmp, rho_new, lane == 0);
-                        lb_head = (lb_head + mem >= mem1) ? lb_head + mem - mem1 : lb_head + mem;
-                        lb_gamma = (1.0 / rho_new) / yy;
+                        sts1_if(W.a_rho() + 8u * tmp, rho_new, lane == 0);
+                        lb_head = tmp;  // rotate_right(1): the staging slot becomes slot 0
+                        sput(H_LBG, (1.0 / rho_new) / yy);
                         lb_active = (lb_active + 1 < mem) ? lb_active + 1 : mem;
                     }
                 }
                 __syncwarp();
-                if (iteration == 0) {
+                if (__builtin_expect(iteration == 0, 0)) {
                     // group 0: psi and grad psi at u_half (Lipschitz test, then update_no_linesearch);
                     // the other groups: psi(u) — u was perturbed by the Lipschitz estimate, its cost is stale
 #pragma unroll
                     for (int s = 0; s < S; s++) x[s] = (grp == 0) ? uh[s] : u[s];
-                    pn_eval = pn;
+                    zero_c = false;
                     phase = PH_A;
                     break;
                 }
@@ -1139,7 +1174,7 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                     };
                     auto fwd = [&](int k, const double2(&sv)[S], const double2(&yv)[S], double rho) {
                         const double al = rho * gsum<G>(dot(sv, q));
-                        sts1_if(W.a_alpha + 8u * k, al, lane == 0);
+                        sts1_if(W.a_alpha() + 8u * k, al, lane == 0);
 #pragma unroll
                         for (int s = 0; s < S; s++) {
                             q[s].x = fma(-al, yv[s].x, q[s].x);
@@ -1147,7 +1182,7 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                         }
                     };
                     auto bwd = [&](int k, const double2(&sv)[S], const double2(&yv)[S], double rho) {
-                        const double alk = lds1(W.a_alpha + 8u * k);
+                        const double alk = lds1(W.a_alpha() + 8u * k);
                         const double beta = rho * gsum<G>(dot(yv, q));
                         const double co = alk - beta;
 #pragma unroll
@@ -1161,19 +1196,19 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                     int sl = lb_head;  // physical slot of pair k; k + 1 is the next slot of the ring
                     ldv(a_s0, sl, sa);
                     ldv(a_y0, sl, ya);
-                    rhoa = lds1(W.a_rho + 8u * sl);
+                    rhoa = lds1(W.a_rho() + 8u * sl);
                     int k = 0;
 #pragma unroll 1
                     for (; k + 1 < lb_active; k += 2) {
                         sl = (sl + 1 >= mem1) ? 0 : sl + 1;
                         ldv(a_s0, sl, sb);
                         ldv(a_y0, sl, yb);
-                        rhob = lds1(W.a_rho + 8u * sl);
+                        rhob = lds1(W.a_rho() + 8u * sl);
                         fwd(k, sa, ya, rhoa);
                         sl = (sl + 1 >= mem1) ? 0 : sl + 1;
                         ldv(a_s0, sl, sa);  // (one pair past the end on the last trip: a valid slot, never used)
                         ldv(a_y0, sl, ya);
-                        rhoa = lds1(W.a_rho + 8u * sl);
+                        rhoa = lds1(W.a_rho() + 8u * sl);
                         fwd(k + 1, sb, yb, rhob);
                     }
                     if (k < lb_active) {  // odd count: pair k is in (sa, ya)
@@ -1183,6 +1218,7 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                         sl = (sl == 0) ? mem1 - 1 : sl - 1;
                     }
                     __syncwarp();
+                    const double lb_gamma = sget(H_LBG);
 #pragma unroll
                     for (int s = 0; s < S; s++) {
                         q[s].x = q[s].x * lb_gamma;
@@ -1191,19 +1227,19 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                     // backward: k = lb_active-1 .. 0, sl = slot of pair lb_active-1
                     ldv(a_s0, sl, sa);
                     ldv(a_y0, sl, ya);
-                    rhoa = lds1(W.a_rho + 8u * sl);
+                    rhoa = lds1(W.a_rho() + 8u * sl);
                     k = lb_active - 1;
 #pragma unroll 1
                     for (; k >= 1; k -= 2) {
                         sl = (sl == 0) ? mem1 - 1 : sl - 1;
                         ldv(a_s0, sl, sb);
                         ldv(a_y0, sl, yb);
-                        rhob = lds1(W.a_rho + 8u * sl);
+                        rhob = lds1(W.a_rho() + 8u * sl);
                         bwd(k, sa, ya, rhoa);
                         sl = (sl == 0) ? mem1 - 1 : sl - 1;
                         ldv(a_s0, sl, sa);
                         ldv(a_y0, sl, ya);
-                        rhoa = lds1(W.a_rho + 8u * sl);
+                        rhoa = lds1(W.a_rho() + 8u * sl);
                         bwd(k - 1, sb, yb, rhob);
                     }
                     if (k == 0) bwd(0, sa, ya, rhoa);
@@ -1216,20 +1252,21 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
 #endif
                 // ONE call: group 0 evaluates psi(u_half), groups 1.. the trials tau = 1, 1/2, ...
                 e0 = 0;
-                gfirst = 1;
-                form_trials(uh);
+                flags |= F_GFIRST;
+                form_trials();
                 phase = PH_A;
                 break;
             }
             case PH_STEP_DONE: {
-                if (!cont) {
+                if (!(flags & F_CONT)) {
                     phase = PH_SOLVE_END;
                     continue;
                 }
-                num_iter++;
-                cont = num_iter < cfg.max_inner_iterations;
-                if (t_budget && nm_globaltimer() - t_begin > t_budget) {  // PANOCOptimizer::solve: time ran out
-                    timed_out = true;
+                const int num_iter = iget(I_NUMIT) + 1;
+                iput(I_NUMIT, num_iter);
+                if (!(num_iter < cfg.max_inner_iterations)) flags &= ~F_CONT;
+                if (out_of_time()) {  // PANOCOptimizer::solve: time ran out
+                    flags |= F_TIMEOUT;
                     phase = PH_SOLVE_END;
                     continue;
                 }
@@ -1237,22 +1274,28 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                 continue;
             }
             case PH_SOLVE_END: {
-                inner_total += num_iter;
+                iput(I_INNER, iget(I_INNER) + iget(I_NUMIT));
+                double2 u[S];
+                W.ld(V_U, u);
                 bool fin = true;
 #pragma unroll
                 for (int s = 0; s < S; s++) fin = fin && isfinite(u[s].x) && isfinite(u[s].y);
                 if (!__all_sync(FULL, fin)) {
-                    status = NMPC_NOT_FINITE;
+                    iput(I_STATUS, NMPC_NOT_FINITE);
                     phase = PH_EXIT;
                     continue;
                 }
                 W.ld(V_UHALF, u);
-                inner_status = timed_out ? NMPC_NOT_CONVERGED_OUT_OF_TIME : (cont ? NMPC_CONVERGED : NMPC_NOT_CONVERGED_ITERATIONS);
-                status = inner_status;
+                __syncwarp();
+                W.st(V_U, u);
+                const int inner_status = (flags & F_TIMEOUT) ? NMPC_NOT_CONVERGED_OUT_OF_TIME
+                                                             : ((flags & F_CONT) ? NMPC_CONVERGED : NMPC_NOT_CONVERGED_ITERATIONS);
+                iput(I_ISTATUS, inner_status);
+                iput(I_STATUS, inner_status);
                 // F2(u) for the outer loop (group 0) and f(u) = psi with c = 0 (group 1), should this be the end
 #pragma unroll
                 for (int s = 0; s < S; s++) x[s] = u[s];
-                pn_eval = (grp == 1) ? make_pen(0.0) : pn;
+                zero_c = (grp == 1);
                 phase = PH_F2;
                 break;
             }
@@ -1265,16 +1308,18 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                         prof_out[8 + i] = W.pt[i];
                     }
 #endif
+                const int status = iget(I_STATUS);
+                const double c = sget(H_PENC);
                 st_out.exit_status = status;
-                st_out.outer_iterations = num_outer;
-                st_out.inner_iterations = inner_total;
-                st_out.last_norm_fpr = norm_fpr;
-                st_out.delta_y_norm_over_c = sget(H_DYNP) / pn.c;
+                st_out.outer_iterations = iget(I_NOUTER);
+                st_out.inner_iterations = iget(I_INNER);
+                st_out.last_norm_fpr = sget(H_NFPR);
+                st_out.delta_y_norm_over_c = sget(H_DYNP) / c;
                 st_out.f2_norm = sget(H_F2NP);
-                st_out.penalty = pn.c;
+                st_out.penalty = c;
                 if (status == NMPC_NOT_FINITE) st_out.cost = CUDART_NAN;
-                st_out.n_cost_evals = n_cost;
-                st_out.n_grad_evals = n_grad;
+                st_out.n_cost_evals = iget(I_NCOST);
+                st_out.n_grad_evals = iget(I_NGRAD);
                 st_out.reserved = 0;
                 return status;
             }
@@ -1287,7 +1332,7 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
 #ifdef NMPC_PROFILE
         const long long tp0 = clock64();
 #endif
-        const double psi = W.eval(x, pn_eval, g, pen, nullptr);
+        const double psi = W.eval(x, zero_c, g, pen, nullptr);
 #ifdef NMPC_PROFILE
         prof[0] += clock64() - tp0;
         prof[1]++;
@@ -1298,11 +1343,12 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
         // ------------------------------------------------------------------ post
         switch (phase) {
             case PH_INIT: {  // group 0: cost / gradient at u; group 1: gradient at u + h -> local Lipschitz estimate
-                cost = __shfl_sync(FULL, psi, 0);
+                sput(H_COST, __shfl_sync(FULL, psi, 0));
                 W.st(V_GRAD, g, 0);
                 W.st(V_T0, g, 1);
                 __syncwarp();
-                double2 gr[S], gh[S], gs[S], uh[S];
+                double2 u[S], gr[S], gh[S], gs[S], uh[S];
+                W.ld(V_U, u);
                 W.ld(V_GRAD, gr);
                 W.ld(V_T0, gh);
                 const double lip = sqrt(gsum<G>(diff2(gh, gr))) / sget(H_NORMH);
@@ -1312,29 +1358,29 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                 W.st(V_GSTEP, gs);
                 W.st(V_UHALF, uh);
                 __syncwarp();
-                n_grad += 2;
-                num_iter = 0;
-                cont = true;
-                timed_out = false;
+                iput(I_NGRAD, iget(I_NGRAD) + 2);
+                iput(I_NUMIT, 0);
+                flags = (flags | F_CONT) & ~F_TIMEOUT;
                 phase = PH_STEP_BEGIN;
                 break;
             }
             case PH_A: {  // first call of an iteration: group 0 holds psi(u_half), the other groups trials (or psi(u))
                 const double cost_half = __shfl_sync(FULL, psi, 0);
-                if (iteration == 0) cost = __shfl_sync(FULL, psi, G);
-                n_cost += 2;  // psi(u_half) and OpEn's re-evaluation of psi(u) (bit-identical to the cached cost)
-                if (lip_test_fails(cost_half)) {
+                if (iteration == 0) sput(H_COST, __shfl_sync(FULL, psi, G));
+                iput(I_NCOST, iget(I_NCOST) + 2);  // psi(u_half) and OpEn's re-evaluation of psi(u) (bit-identical to the cached cost)
+                if (__builtin_expect(lip_test_fails(cost_half), 0)) {
                     lip_halve();
                     break;
                 }
-                if (iteration == 0) {
+                if (__builtin_expect(iteration == 0, 0)) {
                     first_iteration_update(cost_half);
                     break;
                 }
-                if (fbe_valid) {
+                if (flags & F_FBE) {
                     // the envelope at u is the accepted trial's left-hand side of the previous line search
                     // (same cost, gradient, gamma and stored gstep/uhalf: bit-identical), unless gamma changed
-                    rhs_ls = fbe_u - sigma * (norm_fpr * norm_fpr);
+                    const double nf = sget(H_NFPR);
+                    sput(H_RHSLS, sget(H_FBEU) - sget(H_SIGMA) * (nf * nf));
                 } else {
                     rhs_from_envelope();
                 }
@@ -1344,53 +1390,54 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                 grad_step_half(x, g, gs, uh);
                 double d2 = diff2(gs, uh), gg = dot(g, g);
                 gsum2<G>(d2, gg);
-                const double lhs = psi - (0.5 * gamma) * gg + (0.5 * d2) * inv_gamma;
+                const double lhs = psi - (0.5 * sget(H_GAMMA)) * gg + (0.5 * d2) * sget(H_INVG);
+                const int gfirst = (flags & F_GFIRST) ? 1 : 0;
                 int e = e0 + grp - gfirst;  // this group's trial
                 // linesearch(): the first trial with lhs <= rhs is kept; the trial after MAX halvings is kept anyway
-                const bool ok = grp >= gfirst && (!(lhs > rhs_ls) || e >= MAX_LINESEARCH_ITERATIONS);
+                const bool ok = grp >= gfirst && (!(lhs > sget(H_RHSLS)) || e >= MAX_LINESEARCH_ITERATIONS);
                 const unsigned m = __ballot_sync(FULL, ok);
                 if (m) {
                     const int src = __ffs(m) - 1;  // first lane of the accepting group
                     const int k = src / G;
                     e = e0 + k - gfirst;
-                    n_grad += (e > MAX_LINESEARCH_ITERATIONS ? MAX_LINESEARCH_ITERATIONS : e) + 1;
+                    iput(I_NGRAD, iget(I_NGRAD) + (e > MAX_LINESEARCH_ITERATIONS ? MAX_LINESEARCH_ITERATIONS : e) + 1);
                     __syncwarp();
                     W.st(V_U, x, k);
                     W.st(V_GRAD, g, k);
                     W.st(V_GSTEP, gs, k);
                     W.st(V_UHALF, uh, k);
-                    cost = __shfl_sync(FULL, psi, src);
-                    fbe_u = __shfl_sync(FULL, lhs, src);
-                    fbe_valid = true;
+                    sput(H_COST, __shfl_sync(FULL, psi, src));
+                    sput(H_FBEU, __shfl_sync(FULL, lhs, src));
+                    flags |= F_FBE;
                     __syncwarp();
-                    W.ld(V_U, u);
                     iteration++;
                     phase = PH_STEP_DONE;
                 } else {
                     e0 += NG - gfirst;
-                    gfirst = 0;
-                    form_trials(uh);
+                    flags &= ~F_GFIRST;
+                    form_trials();
                     phase = PH_LS;
                 }
                 break;
             }
             case PH_RETRY: {  // psi(u_half) after a halving of gamma (every group evaluated the same point)
                 const double cost_half = psi;
-                n_cost++;
-                double2 uh[S], fpr[S], gr[S];
+                iput(I_NCOST, iget(I_NCOST) + 1);
+                double2 u[S], uh[S], fpr[S], gr[S];
+                W.ld(V_U, u);
                 W.ld(V_UHALF, uh);
                 W.ld(V_GRAD, gr);
-                compute_fpr(uh, fpr);
+                compute_fpr(u, uh, fpr);
                 __syncwarp();
                 W.st(V_FPR, fpr);
-                ip = gsum<G>(dot(gr, fpr));
-                it_lip++;
+                sput(H_IP, gsum<G>(dot(gr, fpr)));
+                iput(I_ITLIP, iget(I_ITLIP) + 1);
                 if (lip_test_fails(cost_half)) {
                     lip_halve();
                     break;
                 }
                 // lbfgs update_hessian on the emptied buffer: remember (u, fpr)
-                lb_first = 0;
+                flags &= ~F_LBFIRST;
                 W.st(V_OLDS, u);
                 W.st(V_OLDG, fpr);
                 if (iteration == 0) {
@@ -1401,14 +1448,17 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                 __syncwarp();
                 rhs_from_envelope();
                 e0 = 0;
-                gfirst = 0;
-                form_trials(uh);
+                flags &= ~F_GFIRST;
+                form_trials();
                 phase = PH_LS;
                 break;
             }
             case PH_F2: {  // multipliers y+ = y + c*(F1 - Proj_C(F1 + y/c)); infeasibilities; outer-loop logic
                 const double f_cost = __shfl_sync(FULL, psi, G);  // group 1 evaluated with c = 0
-                double2 yl[S], yp[S];
+                const int nf2 = cfg.Nobs + cfg.Ndynobs;
+                const double c = sget(H_PENC), inv_ts = W.hdr(H_INVTS);
+                double2 u[S], yl[S], yp[S];
+                W.ld(V_U, u);
                 W.ld(V_YL, yl);
                 double e = 0.0;
                 {
@@ -1418,13 +1468,13 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                     for (int s = 0; s < S; s++) {
                         const double vp = (s == 0) ? vp0 : u[s > 0 ? s - 1 : 0].x, wp_ = (s == 0) ? wp0 : u[s > 0 ? s - 1 : 0].y;
                         const double wa = (u[s].x - vp) * inv_ts, ww = (u[s].y - wp_) * inv_ts;
-                        double za = wa + yl[s].x / pn.c, zw = ww + yl[s].y / pn.c;
+                        double za = wa + yl[s].x / c, zw = ww + yl[s].y / c;
                         za = clampd(za, cfg.lin_acc_min, cfg.lin_acc_max);
                         zw = clampd(zw, -cfg.ang_acc_max, cfg.ang_acc_max);
-                        yp[s].x = W.act[s] ? fma(pn.c, wa - za, yl[s].x) : 0.0;
-                        yp[s].y = W.act[s] ? fma(pn.c, ww - zw, yl[s].y) : 0.0;
+                        yp[s].x = W.act(s) ? fma(c, wa - za, yl[s].x) : 0.0;
+                        yp[s].y = W.act(s) ? fma(c, ww - zw, yl[s].y) : 0.0;
                         const double d0 = yp[s].x - yl[s].x, d1 = yp[s].y - yl[s].y;
-                        const double t = W.act[s] ? fma(d1, d1, d0 * d0) : 0.0;
+                        const double t = W.act(s) ? fma(d1, d1, d0 * d0) : 0.0;
                         e = (s == 0) ? t : e + t;
                     }
                 }
@@ -1432,7 +1482,8 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                 const double akkt_tol = sget(H_AKKT);
                 sput(H_DYNP, dynp);
                 sput(H_F2NP, f2np);
-                const bool crit1 = alm_iter > 0 && dynp <= pn.c * cfg.delta_tolerance + DBL_EPS;
+                const int alm_iter = iget(I_ALM), num_outer = iget(I_NOUTER);
+                const bool crit1 = alm_iter > 0 && dynp <= c * cfg.delta_tolerance + DBL_EPS;
                 const bool crit2 = (nf2 == 0) || f2np <= cfg.delta_tolerance + DBL_EPS;
                 const bool crit3 = akkt_tol <= cfg.tolerance + DBL_EPS;
                 bool finished = crit1 && crit2 && crit3;
@@ -1444,27 +1495,27 @@ __device__ int solve_problem(Warp<G, S>& W, double2 (&u)[S], nmpc_stats& st_out,
                         const bool cp = f2np <= cfg.sufficient_decrease_coeff * sget(H_F2N) + DBL_EPS;
                         stall = (nf2 > 0) ? (ca && cp) : ca;
                     }
-                    if (!stall) pn = make_pen(pn.c * cfg.penalty_update_factor);
+                    if (!stall) {
+                        const double cn = c * cfg.penalty_update_factor;
+                        sput(H_PENC, cn);
+                        sput(H_PINV, 1.0 / fmax(cn, 1.0));
+                    }
                     sput(H_AKKT, fmax(akkt_tol * cfg.inner_tolerance_update, cfg.tolerance));
-                    alm_iter++;
+                    iput(I_ALM, alm_iter + 1);
                     sput(H_DYN, dynp);
                     sput(H_F2N, f2np);
                     __syncwarp();
                     W.st(V_YL, yp);
                     __syncwarp();
                     if (num_outer >= cfg.max_outer_iterations) {
-                        status = NMPC_NOT_CONVERGED_ITERATIONS;
+                        iput(I_STATUS, NMPC_NOT_CONVERGED_ITERATIONS);
                         finished = true;
                     }
                 } else if (num_outer == cfg.max_outer_iterations) {
-                    status = NMPC_NOT_CONVERGED_ITERATIONS;
+                    iput(I_STATUS, NMPC_NOT_CONVERGED_ITERATIONS);
                 }
                 st_out.cost = f_cost;
-                if (finished) {
-                    phase = PH_EXIT;
-                } else {
-                    phase = PH_OUTER_BEGIN;
-                }
+                phase = finished ? PH_EXIT : PH_OUTER_BEGIN;
                 break;
             }
             default:

@@ -18,13 +18,13 @@
 // Warps (problems in flight) per SM.  One CTA per SM; the cap is what the register file allows for each
 // instantiation (32 * cap threads per CTA bound the registers per thread through __launch_bounds__).
 #ifndef NMPC_WARPS
-#define NMPC_WARPS 8  // two warps per SM sub-partition: 255 registers per thread; three (12 warps, 168 registers) spill and lose 30 %
+#define NMPC_WARPS 12  // three warps per SM sub-partition (168 registers per thread); 8 (255 registers) is 10 % slower at saturation
 #endif
 __host__ __device__ constexpr int warps_cap(int G, int S) {
     return (G == 8 || S <= 2) ? NMPC_WARPS : (S == 3 ? 8 : (S == 4 ? 6 : 4));
 }
 
-// load (u0, y0) of problem b: u into registers (every group holds the vector), y into the arena
+// load (u0, y0) of problem b into the arena (V_U, V_YL); u also stays in registers (every group holds the vector)
 template <int G, int S>
 __device__ __forceinline__ void load_start(const KArgs& a, Warp<G, S>& W, int b, double2 (&u)[S]) {
     const int N = W.N;
@@ -33,10 +33,11 @@ __device__ __forceinline__ void load_start(const KArgs& a, Warp<G, S>& W, int b,
     double2 yl[S];
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        const int t = W.tix[s];
+        const int t = W.tix(s);
         u[s] = (t < N) ? *reinterpret_cast<const double2*>(U0 + 2 * t) : make_double2(0.0, 0.0);
         yl[s] = (t < N && Y0) ? make_double2(Y0[t], Y0[N + t]) : make_double2(0.0, 0.0);
     }
+    W.st(V_U, u);
     W.st(V_YL, yl);
     __syncwarp();
 }
@@ -64,21 +65,25 @@ __global__ void __launch_bounds__(32 * warps_cap(G, S), 1) nmpc_solve_kernel(con
         if (b >= a.B) break;  // queue empty
         if (a.skip && a.skip[b]) continue;
         W.stage(a.P + (size_t)b * a.np);
-        double2 u[S];
-        load_start<G, S>(a, W, b, u);
+        {
+            double2 u0[S];
+            load_start<G, S>(a, W, b, u0);
+        }
         nmpc_stats st;
         st.cost = 0.0;
 #ifdef NMPC_PROFILE
-        const int status = solve_problem<G, S>(W, u, st, a.dbg ? a.dbg + (size_t)b * 48 : nullptr);
+        const int status = solve_problem<G, S>(W, st, a.dbg ? a.dbg + (size_t)b * 48 : nullptr);
 #else
-        const int status = solve_problem<G, S>(W, u, st);
+        const int status = solve_problem<G, S>(W, st);
 #endif
+        __syncwarp();
         if (W.grp == 0) {
-            double2 yl[S];
+            double2 u[S], yl[S];
+            W.ld(V_U, u);
             W.ld(V_YL, yl);
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                const int t = W.tix[s];
+                const int t = W.tix(s);
                 if (t < N) {
                     *reinterpret_cast<double2*>(a.U + (size_t)b * 2 * N + 2 * t) = u[s];
                     if (a.Y) {
@@ -107,15 +112,16 @@ __global__ void __launch_bounds__(32 * warps_cap(G, S), 1) nmpc_probe_kernel(con
     const Lay L = make_layout(cfg.N_hor, cfg.Nobs, cfg.Ndynobs);
     const int wpb = blockDim.x >> 5;
     Warp<G, S> W(cfg, L, warp, lane);
-    const Pen pn = make_pen(cfg.initial_penalty);
     for (int b = blockIdx.x * wpb + warp; b < a.B; b += gridDim.x * wpb) {
         int bucket = PROBE_BUCKETS - 1;  // skipped rows go last
         if (!(a.skip && a.skip[b])) {
             W.stage(a.P + (size_t)b * a.np);
             double2 u[S], g[S];
             load_start<G, S>(a, W, b, u);
+            sts1(W.a_hdr + 8u * H_PENC, cfg.initial_penalty);
+            sts1(W.a_hdr + 8u * H_PINV, 1.0 / fmax(cfg.initial_penalty, 1.0));
             double pen;
-            W.eval(u, pn, g, pen, nullptr);
+            W.eval(u, false, g, pen, nullptr);
             double e = fma(g[0].y, g[0].y, g[0].x * g[0].x);
 #pragma unroll
             for (int s = 1; s < S; s++) e = e + fma(g[s].y, g[s].y, g[s].x * g[s].x);
@@ -169,9 +175,10 @@ __global__ void __launch_bounds__(32 * warps_cap(G, S), 1) nmpc_eval_kernel(cons
         if (F2g)
             for (int k = lane; k < nf2; k += 32) F2g[k] = 0.0;  // slots nobody is inside of report exactly 0
         __syncwarp();
-        const Pen pn = make_pen(a.cvec[b]);
+        sts1(W.a_hdr + 8u * H_PENC, a.cvec[b]);
+        sts1(W.a_hdr + 8u * H_PINV, 1.0 / fmax(a.cvec[b], 1.0));
         double pen;
-        const double psi = W.eval(u, pn, g, pen, F2g);
+        const double psi = W.eval(u, false, g, pen, F2g);
         if (lane == 0 && a.psi) a.psi[b] = psi;
         const double inv_ts = W.hdr(H_INVTS);
         double vp0, wp0;
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(32 * warps_cap(G, S), 1) nmpc_eval_kernel(cons
         if (W.grp == 0) {
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                const int t = W.tix[s];
+                const int t = W.tix(s);
                 const double vp = (s == 0) ? vp0 : u[s > 0 ? s - 1 : 0].x, wp_ = (s == 0) ? wp0 : u[s > 0 ? s - 1 : 0].y;
                 if (t < N) {
                     if (a.grad) {

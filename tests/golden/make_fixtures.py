@@ -149,6 +149,7 @@ def record_runs(config, graphs, PathGenerator):
     UNMODIFIED PathGenerator.run with the oracle-backed manager."""
     out = {k: [] for k in ("P", "U0", "Y0", "U", "Y", "status", "inner", "outer", "n_grad", "n_cost", "map", "step")}
     summary = []
+    ctrl, ctrl_map = [], []     # every applied control (v, omega) of every run: lets a test re-walk the whole run
     for cx in range(1, 13):
         g = graphs.get_graph(cx)
         pg = PathGenerator(config, build=False, sinus_object=(cx == 12))
@@ -163,6 +164,7 @@ def record_runs(config, graphs, PathGenerator):
             for key in ("P", "U0", "Y0", "U", "Y", "status", "inner", "outer", "n_grad", "n_cost"):
                 out[key].append(lg[key][k])
             out["map"].append(cx); out["step"].append(k)
+        ctrl.extend(zip(uv, uomega)); ctrl_map.extend([cx] * len(uv))
         P = np.array(lg["P"])
         N, Nobs, Nd = config.N_hor, config.Nobs, config.Ndynobs
         circ = P[:, 20 + N:20 + N + 3 * Nobs].reshape(K, Nobs, 3)
@@ -176,6 +178,7 @@ def record_runs(config, graphs, PathGenerator):
     np.savez_compressed(os.path.join(HERE, "ref_runs.npz"),
                         **{k: np.array(v, dtype=(np.int32 if k in ("status", "inner", "outer", "n_grad", "n_cost", "map", "step") else np.float64))
                            for k, v in out.items()},
+                        ctrl=np.array(ctrl, dtype=np.float64), ctrl_map=np.array(ctrl_map, dtype=np.int32),
                         summary=np.array([[s[0], s[1], s[2], s[4], s[5], int(s[6])] for s in summary], dtype=np.int32))
 
 

@@ -15,6 +15,11 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-4   # north_star: "trajectories within 1e-4 rel-L2"
 
 
+def same(a, b):
+    """bit-for-bit equality; a solve that ends NotFiniteComputation leaves NaNs in its reply on both sides"""
+    return np.array_equal(a, b, equal_nan=True)
+
+
 def _cfgs(pkg, oracle, **kw):
     g = pkg.NmpcConfig.default(**kw)
     o = oracle.default_config(**kw)
@@ -222,9 +227,9 @@ def test_config2_workload_full_batch_parity(oracle, gpu_solver_factory):
 @pytest.mark.parametrize("N,Nobs,B", [(20, 10, 1), (20, 10, 2), (20, 10, 3), (20, 10, 5), (20, 10, 13), (20, 10, 37),
                                       (20, 10, 900), (40, 10, 3), (40, 10, 11), (80, 50, 2), (80, 200, 4)])
 def test_small_batches_with_idle_warps(oracle, gpu_solver_factory, N, Nobs, B):
-    """Batches that leave warps of a CTA without a problem: those warps evaluate line-search trials (and, in the
-    latency instantiation, psi(uhalf)) of the others.  Who evaluates must not change a bit: replies, multipliers,
-    iteration and evaluation counts against the oracle, twice in a row (timing differs between launches)."""
+    """Batches smaller than the machine (first wave only, CTAs with idle warps) with obstacles in the way (the
+    penalty slow paths, Lipschitz halvings, exhausted line searches): replies, multipliers, iteration and evaluation
+    counts against the oracle, twice in a row."""
     import mpc_trajectory_generator_b200 as pkg
     g, o = _cfgs(pkg, oracle, N_hor=N, Nobs=Nobs, Ndynobs=3)
     P = problems.synth(N, Nobs, 3, B, seed=1000 + B + N, active=True)
@@ -233,7 +238,7 @@ def test_small_batches_with_idle_warps(oracle, gpu_solver_factory, N, Nobs, B):
     for _ in range(2):
         U, Y, st, stats = s.solve_batch(P)
         assert np.array_equal(st, sto)
-        assert np.array_equal(U, Uo) and np.array_equal(Y, Yo)
+        assert same(U, Uo) and same(Y, Yo)
         for k in ("inner_iterations", "outer_iterations", "n_grad_evals", "n_cost_evals"):
             assert np.array_equal(stats[k], statso[k]), k
 
