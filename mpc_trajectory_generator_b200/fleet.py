@@ -74,8 +74,10 @@ class FleetPlan:
             n = len(s.x_ref)
             n_ref[b] = n
             ref[b, :n, 0], ref[b, :n, 1], ref[b, :n, 2] = s.x_ref, s.y_ref, s.theta_ref
-            n_vert[b] = len(s.vert)
-            if len(s.vert):
+            # the reference fills the circle slots only on maps that have obstacles (src/path_generator.py:295):
+            # corner vertices of an obstacle-free, non-convex boundary are never sent
+            n_vert[b] = len(s.vert) if len(s.obstacles) else 0
+            if n_vert[b]:
                 vert[b, :len(s.vert)] = np.asarray(s.vert, dtype=np.float64)
             start[b] = s.start
             goal[b] = s.end
@@ -90,6 +92,9 @@ class FleetPlan:
                 raise NmpcError("fleet stepping needs 0 or exactly Ndynobs dynamic obstacles on the map")
             if cfg.num_steps_taken != 1:
                 raise NmpcError("fleet stepping implements num_steps_taken = 1")
+            if max_steps <= 0:
+                raise NmpcError("this map has dynamic obstacles: from_scenarios needs max_steps (the number of steps the "
+                                "fleet may run) to size their schedule")
             # entry m of the ring: the t=0 fill (np.linspace(0, N*ts, N), src/visibility/visibility.py:204) for m < N,
             # afterwards the entry appended at step m-N+1 for time (m) * ts (src/path_generator.py:318-326)
             init = sc0._dyn_obstacles(0 * cfg.ts, N)

@@ -15,7 +15,8 @@ from .solver import NmpcConfig
 _FLOAT_FIELDS = ["ts", "lin_vel_min", "lin_vel_max", "ang_vel_max", "lin_acc_min", "lin_acc_max", "ang_acc_max",
                  "tolerance", "initial_tolerance", "delta_tolerance", "inner_tolerance_update",
                  "penalty_update_factor", "initial_penalty", "sufficient_decrease_coeff"]
-_INT_FIELDS = ["N_hor", "Nobs", "Ndynobs", "lbfgs_memory", "max_inner_iterations", "max_outer_iterations"]
+_INT_FIELDS = ["N_hor", "Nobs", "Ndynobs", "lbfgs_memory", "max_inner_iterations", "max_outer_iterations",
+               "max_duration_micros"]
 
 
 def shard_bounds(B, world, rank):

@@ -1,0 +1,92 @@
+"""Solve-level pin that is independent of the kernel's arithmetic contract.
+
+oracle/libnmpc_oracle_serial.so is the same control flow compiled with the REFERENCE's arithmetic
+(src/mpc/mpc_generator.py:81-148: libm sin/cos, true divisions, separate multiply and add, the rollout as the literal
+recurrence, every sum a serial loop): it shares no reduction order, no sincos and no reciprocal with the CUDA kernel.
+north_star asks for trajectories within 1e-4 rel-L2; the tests hold the contract oracle (CPU) and the CUDA solver
+(GPU) to that bar against the serial build on every problem BOTH sides solve to convergence, and report what
+happens to the rest: a solve that runs into the iteration budget follows a chaotic path, so its reply — and, for
+under 1 % of the problems, even its exit flag — depends on the last bits of the arithmetic, in OpEn as in here."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REL_TOL = 1e-4
+
+
+def _compare(U, st, Us, sts, min_converged):
+    both = (st == 0) & (sts == 0)
+    rel = np.linalg.norm(U - Us, axis=1) / np.maximum(np.linalg.norm(Us, axis=1), 1e-12)
+    assert both.sum() >= min_converged
+    assert rel[both].max() <= REL_TOL, f"converged problems differ by {rel[both].max():.2e}"
+    flag_mismatch = float((st != sts).mean())
+    assert flag_mismatch <= 0.02, f"{flag_mismatch:.3%} of the exit flags differ"
+    assert not np.any((st == 3) | (sts == 3))
+    rest = ~both
+    return {"converged_both": int(both.sum()), "max_rel_converged": float(rel[both].max()),
+            "flag_mismatch": flag_mismatch, "rest": int(rest.sum()),
+            "rest_within_tol": int((rel[rest] <= REL_TOL).sum()) if rest.any() else 0}
+
+
+def _config2(n):
+    from mpc_trajectory_generator_b200 import workloads
+    from mpc_trajectory_generator_b200.host import assembly
+    P, _ = workloads.first_step_batch(assembly.HostConfig.default(), complexity=3, B=n, seed=0)
+    return P
+
+
+def test_contract_oracle_vs_serial_arithmetic_reference_runs(oracle):
+    """every recorded solver call of the reference's twelve runs, from its recorded warm start"""
+    g = np.load(os.path.join(GOLD, "ref_runs.npz"))
+    cfg = oracle.default_config()
+    Us, Ys, sts, _ = oracle.solve_batch(cfg, g["P"], g["U0"], g["Y0"], serial=True)
+    r = _compare(g["U"], g["status"], Us, sts, min_converged=400)
+    print("reference runs:", r)
+
+
+def test_contract_oracle_vs_serial_arithmetic_config2(oracle):
+    """BASELINE config 2 (first-step problems on map 3, cold start): 768 problems, >= 256 converged on both sides"""
+    P = _config2(768)
+    cfg = oracle.default_config()
+    U, Y, st, _ = oracle.solve_batch(cfg, P)
+    Us, Ys, sts, _ = oracle.solve_batch(cfg, P, serial=True)
+    r = _compare(U, st, Us, sts, min_converged=256)
+    print("config 2:", r)
+
+
+def test_serial_build_cost_and_gradient_vs_autograd(oracle):
+    """the serial build's psi / grad psi against the torch-autograd restatement of the reference's CasADi graph"""
+    import nmpc_problems as problems
+    from oracle import oracle_np
+    cfg = oracle.default_config()
+    B = 4
+    P = problems.synth(20, 10, 3, B, seed=77)
+    U = problems.random_controls(20, B, seed=5)
+    Y = np.random.default_rng(3).normal(0, 2.0, (B, 40))
+    c = np.array([1.0, 5.0, 25.0, 125.0])
+    psi, grad, F1, F2 = oracle.eval_batch(cfg, P, U, c, Y, serial=True)
+    cd = oracle_np.cfg_dict(cfg)
+    for b in range(B):
+        v, g, f1, f2 = oracle_np.eval_psi(U[b], P[b], c[b], Y[b], cd)
+        assert abs(v - psi[b]) <= 1e-12 * abs(v)
+        assert np.abs(g - grad[b]).max() <= 1e-10 * max(1.0, np.abs(g).max())
+        assert np.abs(f2 - F2[b]).max() <= 1e-11
+
+
+@pytest.mark.gpu
+def test_gpu_vs_serial_arithmetic(oracle, gpu_solver_factory):
+    """The CUDA solver against the serial-arithmetic build: the recorded reference runs (from their warm starts) and
+    1024 problems of BASELINE config 2."""
+    import mpc_trajectory_generator_b200 as pkg
+    s = gpu_solver_factory(pkg.NmpcConfig.default())
+    cfg = oracle.default_config()
+    g = np.load(os.path.join(GOLD, "ref_runs.npz"))
+    U, Y, st, _ = s.solve_batch(g["P"], g["U0"], g["Y0"])
+    Us, Ys, sts, _ = oracle.solve_batch(cfg, g["P"], g["U0"], g["Y0"], serial=True)
+    print("reference runs:", _compare(U, st, Us, sts, min_converged=400))
+    P = _config2(1024)
+    U, Y, st, _ = s.solve_batch(P)
+    Us, Ys, sts, _ = oracle.solve_batch(cfg, P, serial=True)
+    print("config 2:", _compare(U, st, Us, sts, min_converged=256))
