@@ -181,8 +181,9 @@ int nmpc_eval_batch(nmpc_handle* h, int32_t B, const double* P, const double* U,
  *             run the termination test (src/path_generator.py:397).
  * n steps are enqueued back to back on the handle's stream without a host round trip.  Fleets larger than the GPU's
  * warp slots are solved longest-first (by each robot's iteration count in the previous step): scheduling only.
- * Restrictions (documented deviations): num_steps_taken = 1 (configs/default.yaml:17); a map has either
- * no dynamic obstacles (phantom unit discs, src/path_generator.py:274-280) or exactly Ndynobs of them.
+ * num_steps_taken controls are applied per solve (configs/default.yaml:17; smooth_velocity.yaml uses 2); a map may
+ * have 0 .. Ndynobs dynamic obstacles (unused slots are the reference's phantom unit discs,
+ * src/path_generator.py:274-280, including what its flat-list rotation leaks into them, :312).
  */
 typedef struct nmpc_fleet nmpc_fleet;
 
@@ -193,7 +194,8 @@ typedef struct nmpc_fleet_config {
     int32_t n_brake;   /* entries of the brake profile (get_brake_vel_ref)                       */
     int32_t n_sched;   /* rows of the dynamic-obstacle schedule; 0 = map without dynamic obstacles */
     int32_t log_steps; /* per-robot trajectory log capacity in steps (0 = no log)               */
-    int32_t reserved0, reserved1;
+    int32_t num_steps_taken; /* controls applied per solve, 1 .. N_hor (configs/default.yaml:17); 0 means 1 */
+    int32_t n_dyn;     /* dynamic obstacles the map really has, 1 .. Ndynobs; 0 means Ndynobs (when n_sched > 0) */
     double base_speed;    /* lin_vel_max * throttle_ratio (src/path_generator.py:352)            */
     double circle_radius; /* vehicle_width/2 + vehicle_margin (src/path_generator.py:301)        */
     double goal_tol;      /* 0.05  (src/path_generator.py:397)                                   */
@@ -211,9 +213,12 @@ int nmpc_fleet_destroy(nmpc_fleet* f);
  *   n_vert[B], vert[B, max_vert, 2] original vertices of the A* corners (src/visibility/visibility.py:126-139)
  *   start[B, 3], goal[B, 3]
  *   brake_vel[n_brake], brake_dist[n_brake]     (src/path_generator.py:439-477)
- *   sched_init[N, Ndynobs, 5], sched[n_sched, Ndynobs, 5]  (x, y, rx, ry, angle) of every dynamic obstacle:
+ *   sched_init[N, Ndynobs, 5], sched[n_sched, Ndynobs, 5]  (x, y, rx, ry, angle) of every dynamic obstacle
+ *       (columns >= n_dyn unused): entry m of an obstacle's pose sequence as the reference's ring sees it —
  *       sched_init[m] = entry m of the t=0 fill (np.linspace(0, N*ts, N) times, src/visibility/visibility.py:204),
- *       sched[m]      = the entry appended for time m*ts (m >= N); both NULL when n_sched == 0. */
+ *       sched[m], m >= N = the (m-N)-th pose appended by the loop (src/path_generator.py:313-316: iteration c appends
+ *       num_steps_taken poses at np.linspace((c*s+N-s)*ts, .. + s*ts, s)); rows 0 .. N-1 of sched are unused.
+ *       The fleet refuses to step once a step would read past row n_sched-1.  Both NULL when n_sched == 0. */
 int nmpc_fleet_load(nmpc_fleet* f, const int32_t* n_ref, const double* ref, const int32_t* n_vert,
                     const double* vert, const double* start, const double* goal, const double* brake_vel,
                     const double* brake_dist, const double* sched_init, const double* sched);

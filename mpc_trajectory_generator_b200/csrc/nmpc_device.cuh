@@ -377,11 +377,15 @@ struct Warp {
         for (int s = 0; s < S; s++) r[s] = lds2(la + k * vstride + 16u * G * s);
     }
     // stores come from ONE group (by default group 0; `from` = the group whose registers hold the vector)
+    // (warp barriers on both sides: the other groups may still be reading the vector's previous contents, and
+    //  they read the new ones next)
     __device__ __forceinline__ void st(int k, const double2 (&r)[S], int from = 0) const {
+        __syncwarp();
         if (grp == from) {
 #pragma unroll
             for (int s = 0; s < S; s++) sts2(la + k * vstride + 16u * G * s, r[s]);
         }
+        __syncwarp();
     }
 
     // unpack the parameter row (layout: include/nmpc_b200.h) into the arena

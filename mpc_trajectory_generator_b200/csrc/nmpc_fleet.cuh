@@ -74,17 +74,21 @@ __global__ void __launch_bounds__(256) fleet_assemble_kernel(const __grid_consta
     const double gx = goal[0], gy = goal[1];
     const int t = f.t[b];
 
-    // ---- reference index: closest sample inside [idx-1, idx+5) (src/path_generator.py:330-333)
+    // ---- reference index: closest sample inside [idx - steps, idx + 5*steps) (src/path_generator.py:319-324)
     const int n = f.n_ref[b];
+    const int steps = max(1, f.fc.num_steps_taken);
     const double* __restrict__ R = f.ref + (size_t)b * f.fc.max_ref * 3;
     int idx = f.idx[b];
     {
-        const int lb = max(0, idx - 1), ub = min(n, idx + 5);
+        const int lb = max(0, idx - steps), ub = min(n, idx + 5 * steps);
         double d = CUDART_INF;
         int i = 0x7fffffff;
-        if (lb + lane < ub) {
-            d = dist2(x, y, R[3 * (lb + lane)], R[3 * (lb + lane) + 1]);
-            i = lane;
+        for (int k = lane; lb + k < ub; k += 32) {  // ascending k per lane + strict '<': the first minimum wins
+            const double dk = dist2(x, y, R[3 * (lb + k)], R[3 * (lb + k) + 1]);
+            if (dk < d) {
+                d = dk;
+                i = k;
+            }
         }
         warp_argmin(d, i);
         idx = lb + i;
@@ -161,20 +165,36 @@ __global__ void __launch_bounds__(256) fleet_assemble_kernel(const __grid_consta
         }
     }
 
-    // ---- dynamic ellipses: slot j of the ring at step t holds schedule entry m = t + j
-    //      (the t=0 fill for m < N, the per-step appended entries after; src/path_generator.py:306-326)
+    // ---- dynamic ellipses (src/path_generator.py:306-316).  The reference keeps ONE flat list for all obstacle
+    //      slots, rotates it left by `steps` entries per iteration and overwrites the tail of every REAL obstacle's
+    //      block with its newest poses.  In closed form, with t = plant steps taken so far:
+    //        real obstacle k < n_dyn : slot j holds schedule entry m = t + j of obstacle k (the t=0 fill for m < N,
+    //                                  the appended entries after);
+    //        unused slots k >= n_dyn : phantom unit discs (0,0,1,1,0) (:274-280) — except that the rotation feeds the
+    //                                  entries leaving the front of obstacle 0's block into the END of the flat list:
+    //                                  position q = (k - n_dyn) N + j of the unused region holds entry q + t - Lp of
+    //                                  obstacle 0 once that is >= 0 (Lp = (Nd - n_dyn) N).  Maps without dynamic
+    //                                  obstacles rotate identical phantoms: nothing changes.
     {
         double* __restrict__ pe = p + NMPC_NZ + N + 3 * Nobs;
         const int ne = Nd * N;
+        const int n_dyn = (f.fc.n_sched == 0) ? 0 : ((f.fc.n_dyn > 0) ? min(f.fc.n_dyn, Nd) : Nd);
+        const int Lp = (Nd - n_dyn) * N;
         for (int i = lane; i < ne; i += 32) {
             const int k = i / N, j = i - k * N;
             double* __restrict__ e = pe + 5 * (size_t)i;  // obstacle-major, then time
-            if (f.fc.n_sched == 0) {
-                e[0] = 0.0; e[1] = 0.0; e[2] = 1.0; e[3] = 1.0; e[4] = 0.0;  // phantom unit disc (:274-280)
+            int m = -1, col = 0;
+            if (k < n_dyn) {
+                m = t + j;
+                col = k;
+            } else if (n_dyn > 0) {
+                m = (k - n_dyn) * N + j + t - Lp;
+            }
+            if (m < 0) {
+                e[0] = 0.0; e[1] = 0.0; e[2] = 1.0; e[3] = 1.0; e[4] = 0.0;
             } else {
-                const int m = t + j;
-                const int mm = min(m, f.fc.n_sched - 1);
-                const double* __restrict__ s = (m < N) ? f.sched_init + 5 * ((size_t)m * Nd + k) : f.sched + 5 * ((size_t)mm * Nd + k);
+                const int mm = min(m, f.fc.n_sched - 1);  // (the host refuses to step past the schedule)
+                const double* __restrict__ s = (m < N) ? f.sched_init + 5 * ((size_t)m * Nd + col) : f.sched + 5 * ((size_t)mm * Nd + col);
 #pragma unroll
                 for (int c = 0; c < 5; c++) e[c] = s[c];
             }
@@ -202,26 +222,31 @@ __global__ void __launch_bounds__(256) fleet_advance_kernel(const __grid_constan
         return;
     }
     const int N2 = 2 * f.cfg.N_hor;
-    const double v = f.U[(size_t)b * N2], w = f.U[(size_t)b * N2 + 1];
+    const int steps = max(1, f.fc.num_steps_taken);  // the first `steps` controls of the reply are applied
     double x = f.state[3 * b], y = f.state[3 * b + 1], th = f.state[3 * b + 2];
-    double s, c;
-    nm_sincos(th, s, c);
     const double ts = f.cfg.ts;
-    x = x + ts * (v * c);
-    y = y + ts * (v * s);
-    th = th + ts * w;
+    int t = f.t[b];
+    double v = 0.0, w = 0.0;
+    for (int i = 0; i < steps; i++, t++) {
+        v = f.U[(size_t)b * N2 + 2 * i];
+        w = f.U[(size_t)b * N2 + 2 * i + 1];
+        double s, c;
+        nm_sincos(th, s, c);
+        x = x + ts * (v * c);
+        y = y + ts * (v * s);
+        th = th + ts * w;
+        if (f.log && t < f.fc.log_steps) {
+            double* l = f.log + ((size_t)b * f.fc.log_steps + t) * 5;
+            l[0] = x; l[1] = y; l[2] = th; l[3] = v; l[4] = w;
+            f.n_logged[b] = t + 1;
+        }
+    }
     f.state[3 * b] = x;
     f.state[3 * b + 1] = y;
     f.state[3 * b + 2] = th;
     f.last_u[2 * b] = v;
     f.last_u[2 * b + 1] = w;
-    const int t = f.t[b];
-    f.t[b] = t + 1;
-    if (f.log && t < f.fc.log_steps) {
-        double* l = f.log + ((size_t)b * f.fc.log_steps + t) * 5;
-        l[0] = x; l[1] = y; l[2] = th; l[3] = v; l[4] = w;
-        f.n_logged[b] = t + 1;
-    }
+    f.t[b] = t;
     const double* goal = f.goal + 3 * (size_t)b;
     // np.allclose(states[-3:-1], end[0:2], atol=0.05, rtol=0) and abs(system_input[-2]) < 0.005
     if (fabs(x - goal[0]) <= f.fc.goal_tol && fabs(y - goal[1]) <= f.fc.goal_tol && fabs(v) < f.fc.stop_tol) f.done[b] = 1;

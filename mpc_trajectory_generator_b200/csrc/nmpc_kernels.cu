@@ -656,7 +656,8 @@ int nmpc_fleet_create(nmpc_handle* h, const nmpc_fleet_config* fc, nmpc_fleet** 
     if (!h || !fc || !out) return NMPC_ERR_INVALID;
     *out = nullptr;
     if (fc->n_robots < 1 || fc->max_ref < 1 || fc->max_vert < 0 || fc->n_brake < 1 || fc->n_sched < 0 || fc->log_steps < 0 ||
-        !(fc->base_speed > 0.0))
+        !(fc->base_speed > 0.0) || fc->num_steps_taken < 0 || fc->num_steps_taken > h->cfg.N_hor || fc->n_dyn < 0 ||
+        fc->n_dyn > h->cfg.Ndynobs)
         return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_create: bad fleet config%s", "");
     CUDA_TRY(h, cudaSetDevice(h->device));
     nmpc_fleet* f = new (std::nothrow) nmpc_fleet();
@@ -832,7 +833,9 @@ int nmpc_fleet_step(nmpc_fleet* f, int32_t n_steps) {
     const int B = f->fc.n_robots;
     // step t reads schedule rows t .. t + N - 1 (src/path_generator.py:306-316): refuse to run past the end of
     // the uploaded schedule instead of freezing the obstacles at their last pose
-    if (f->fc.n_sched > 0 && f->steps_done + n_steps + h->cfg.N_hor - 1 > f->fc.n_sched)
+    const int64_t spp = f->fc.num_steps_taken > 0 ? f->fc.num_steps_taken : 1;   // plant steps per solve
+    // with unused obstacle slots the reference's rotation also reads obstacle 0's entries (index + t - Lp < t + N)
+    if (f->fc.n_sched > 0 && (f->steps_done + n_steps - 1) * spp + h->cfg.N_hor > f->fc.n_sched)
         return set_err(h, NMPC_ERR_INVALID, "nmpc_fleet_step: the dynamic-obstacle schedule is too short for this many steps "
                        "(n_sched rows must cover steps + N_hor - 1)%s", "");
     CUDA_TRY(h, cudaEventRecord(h->ev0, s));

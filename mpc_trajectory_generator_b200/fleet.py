@@ -17,7 +17,7 @@ from .solver import NmpcError, _dp, _ip, _ptr, param_len
 class FleetConfig(C.Structure):
     """struct nmpc_fleet_config"""
     _fields_ = [("n_robots", C.c_int32), ("max_ref", C.c_int32), ("max_vert", C.c_int32), ("n_brake", C.c_int32),
-                ("n_sched", C.c_int32), ("log_steps", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+                ("n_sched", C.c_int32), ("log_steps", C.c_int32), ("num_steps_taken", C.c_int32), ("n_dyn", C.c_int32),
                 ("base_speed", C.c_double), ("circle_radius", C.c_double), ("goal_tol", C.c_double),
                 ("stop_tol", C.c_double), ("weights", C.c_double * 10)]
 
@@ -27,7 +27,8 @@ class FleetPlan:
     src/path_generator.py:238-287)."""
 
     def __init__(self, n_ref, ref, n_vert, vert, start, goal, brake_vel, brake_dist, weights, base_speed,
-                 circle_radius, sched_init=None, sched=None, n_nodes=None, nodes=None, ref_speed=None):
+                 circle_radius, sched_init=None, sched=None, n_nodes=None, nodes=None, ref_speed=None,
+                 num_steps_taken=1, n_dyn=0):
         self.n_ref = np.ascontiguousarray(n_ref, dtype=np.int32)
         self.ref = np.ascontiguousarray(ref, dtype=np.float64)
         self.n_vert = np.ascontiguousarray(n_vert, dtype=np.int32)
@@ -46,6 +47,8 @@ class FleetPlan:
         self.n_nodes = None if n_nodes is None else np.ascontiguousarray(n_nodes, dtype=np.int32)
         self.nodes = None if nodes is None else np.ascontiguousarray(nodes, dtype=np.float64)
         self.ref_speed = None if ref_speed is None else float(ref_speed)
+        self.num_steps_taken = int(num_steps_taken)   # controls applied per solve (configs/default.yaml:17)
+        self.n_dyn = int(n_dyn)                       # dynamic obstacles the map really has (0: none, or all slots)
         B = self.n_ref.shape[0]
         assert self.ref.shape[0] == B and self.ref.shape[2] == 3 and self.start.shape == (B, 3)
         assert self.goal.shape == (B, 3) and self.n_vert.shape == (B,) and self.vert.shape[0] == B
@@ -87,29 +90,35 @@ class FleetPlan:
         for b, s in enumerate(scenarios):
             nodes[b, :n_nodes[b]] = np.asarray(s.path[1:], dtype=np.float64)
         sched_init = sched = None
-        if len(sc0.dyn_obs):
-            if len(sc0.dyn_obs) != Nd:
-                raise NmpcError("fleet stepping needs 0 or exactly Ndynobs dynamic obstacles on the map")
-            if cfg.num_steps_taken != 1:
-                raise NmpcError("fleet stepping implements num_steps_taken = 1")
+        steps = int(cfg.num_steps_taken)
+        n_dyn = len(sc0.dyn_obs)
+        if n_dyn:
+            if n_dyn > Nd:
+                raise NmpcError("the map has more dynamic obstacles than the solver has slots (Ndynobs)")
             if max_steps <= 0:
                 raise NmpcError("this map has dynamic obstacles: from_scenarios needs max_steps (the number of steps the "
                                 "fleet may run) to size their schedule")
-            # entry m of the ring: the t=0 fill (np.linspace(0, N*ts, N), src/visibility/visibility.py:204) for m < N,
-            # afterwards the entry appended at step m-N+1 for time (m) * ts (src/path_generator.py:318-326)
+            # An obstacle's pose sequence as the reference's ring sees it: entries 0 .. N-1 are the t=0 fill
+            # (np.linspace(0, N*ts, N), src/visibility/visibility.py:204); loop iteration c >= 1 (plant time t = c*steps)
+            # appends `steps` poses at np.linspace((t+N-steps)*ts, .. + steps*ts, steps) (src/path_generator.py:313-316),
+            # which become entries N + (c-1)*steps .. N + c*steps - 1.
             init = sc0._dyn_obstacles(0 * cfg.ts, N)
             sched_init = np.zeros((N, Nd, 5))
             for k, dob in enumerate(init):
                 sched_init[:, k, :] = np.asarray([[float(v) for v in e] for e in dob])
-            n_sched = N + max_steps + 1
+            n_sched = N + max_steps * steps + steps
             sched = np.zeros((n_sched, Nd, 5))
-            for m in range(N, n_sched):
-                t = m - N + 1     # the step at which the reference appends this entry
-                for k, dob in enumerate(sc0._dyn_obstacles((t + N - 1) * cfg.ts, 1)):
-                    sched[m, k, :] = [float(v) for v in dob[0]]
+            for c in range(1, max_steps + 2):
+                t = c * steps
+                for k, dob in enumerate(sc0._dyn_obstacles((t + N - steps) * cfg.ts, steps)):
+                    for i in range(steps):
+                        m = N + (c - 1) * steps + i
+                        if m < n_sched:
+                            sched[m, k, :] = [float(v) for v in dob[i]]
         return cls(n_ref, ref, n_vert, vert, start, goal, sc0.brake_vel, sc0.brake_dist, sc0.weights,
                    cfg.lin_vel_max * cfg.throttle_ratio, cfg.vehicle_width / 2 + cfg.vehicle_margin, sched_init, sched,
-                   n_nodes=n_nodes, nodes=nodes, ref_speed=cfg.throttle_ratio * 1.1 * cfg.lin_vel_max)
+                   n_nodes=n_nodes, nodes=nodes, ref_speed=cfg.throttle_ratio * 1.1 * cfg.lin_vel_max,
+                   num_steps_taken=steps, n_dyn=n_dyn)
 
 
 class NmpcFleet:
@@ -134,7 +143,8 @@ class NmpcFleet:
         self.log_steps = int(log_steps)
         fc = FleetConfig(n_robots=self.B, max_ref=plan.ref.shape[1], max_vert=plan.vert.shape[1],
                          n_brake=len(plan.brake_vel), n_sched=0 if plan.sched is None else plan.sched.shape[0],
-                         log_steps=self.log_steps, base_speed=plan.base_speed, circle_radius=plan.circle_radius,
+                         log_steps=self.log_steps, num_steps_taken=plan.num_steps_taken, n_dyn=plan.n_dyn,
+                         base_speed=plan.base_speed, circle_radius=plan.circle_radius,
                          goal_tol=goal_tol, stop_tol=stop_tol)
         for i, w in enumerate(plan.weights):
             fc.weights[i] = w

@@ -14,10 +14,12 @@ from mpc_trajectory_generator_b200.fleet import FleetPlan
 from mpc_trajectory_generator_b200.host import assembly
 
 
-def _scenarios(complexity, n, seed, smooth=False, **cfgkw):
+def _scenarios(complexity, n, seed, smooth=False, n_dyn=None, **cfgkw):
     hc = assembly.HostConfig.smooth_velocity(**cfgkw) if smooth else assembly.HostConfig.default(**cfgkw)
     if complexity in (2, 12):   # maps with dynamic obstacles: the map's own start/goal plus nearby variants
-        gmap = assembly.load_maps()[complexity]
+        gmap = dict(assembly.load_maps()[complexity])
+        if n_dyn is not None:   # a map with fewer moving obstacles than the solver has slots
+            gmap["dyn_obs"] = gmap["dyn_obs"][:n_dyn]
         rng = np.random.default_rng(seed)
         out = []
         env = assembly.Scenario.make_env(hc, gmap)
@@ -46,20 +48,34 @@ def test_plan_packing_cpu():
     assert plan.circle_radius == hc.vehicle_width / 2 + hc.vehicle_margin
 
 
-def test_dynamic_schedule_matches_ring_cpu():
-    """the closed form 'ring slot j at step t = schedule entry t+j' against the reference's rotate-and-append ring"""
-    hc, scs = _scenarios(12, 1, seed=0)
+@pytest.mark.parametrize("steps,n_dyn", [(1, 3), (2, 3), (3, 3), (1, 1), (2, 2), (3, 1)])
+def test_dynamic_schedule_matches_ring_cpu(steps, n_dyn):
+    """The closed form the device uses against the reference's rotate-and-append ring (src/path_generator.py:306-316,
+    restated literally by host.assembly.Scenario.parameters): real obstacle k, slot j at plant time t = schedule entry
+    t + j; with unused slots, position q of the unused region holds obstacle 0's entry q + t - Lp once that is >= 0
+    (the rotation of the flat list leaks the front of block 0 into the end of the list)."""
+    hc, scs = _scenarios(12, 1, seed=0, n_dyn=n_dyn, num_steps_taken=steps)
     sc = scs[0]
     N, Nd = hc.N_hor, hc.Ndynobs
-    plan = FleetPlan.from_scenarios(scs, max_steps=30)
+    iters = 30
+    plan = FleetPlan.from_scenarios(scs, max_steps=iters)
+    assert plan.num_steps_taken == steps and plan.n_dyn == n_dyn
     off = 20 + N + 3 * hc.Nobs
-    for t in range(30):
+    Lp = (Nd - n_dyn) * N
+    entry = lambda m, k: plan.sched_init[m, k] if m < N else plan.sched[m, k]  # noqa: E731
+    phantom = np.array([0.0, 0.0, 1.0, 1.0, 0.0])
+    for c in range(iters):
+        t = c * steps
         p = sc.parameters()
         ring = p[off:off + 5 * Nd * N].reshape(Nd, N, 5)
-        for j in range(N):
-            m = t + j
-            src = plan.sched_init[m] if m < N else plan.sched[m]
-            assert np.array_equal(ring[:, j, :], src), (t, j)
+        for k in range(Nd):
+            for j in range(N):
+                if k < n_dyn:
+                    want = entry(t + j, k)
+                else:
+                    m = (k - n_dyn) * N + j + t - Lp
+                    want = entry(m, 0) if m >= 0 else phantom
+                assert np.array_equal(ring[k, j], want), (c, k, j)
         sc.apply(np.zeros(2 * N))   # any input: the ring does not depend on the robot
 
 
@@ -94,11 +110,16 @@ def _oracle_cfg(oracle, hc):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("complexity,B,steps,smooth,N", [(3, 24, 12, False, 20), (12, 6, 25, False, 20), (1, 8, 10, False, 20),
-                                                         (11, 6, 8, True, 40)])   # last: BASELINE config 4's setup
-def test_fleet_steps_match_host_loop(oracle, gpu_solver_factory, complexity, B, steps, smooth, N):
+@pytest.mark.parametrize("complexity,B,steps,smooth,N,taken,n_dyn",
+                         [(3, 24, 12, False, 20, 1, None), (12, 6, 25, False, 20, 1, None), (1, 8, 10, False, 20, 1, None),
+                          (11, 6, 8, True, 40, 1, None),    # BASELINE config 4's setup
+                          (11, 6, 8, True, 40, 2, None),    # smooth_velocity.yaml as shipped: two controls per solve
+                          (12, 4, 14, False, 20, 3, None),  # william_config.yaml's num_steps_taken with moving obstacles
+                          (12, 4, 30, False, 20, 1, 1),     # fewer moving obstacles than slots: the leaking rotation
+                          (2, 4, 12, False, 20, 2, 2)])
+def test_fleet_steps_match_host_loop(oracle, gpu_solver_factory, complexity, B, steps, smooth, N, taken, n_dyn):
     import mpc_trajectory_generator_b200 as pkg
-    hc, scs = _scenarios(complexity, B, seed=10 + complexity, smooth=smooth, N_hor=N)
+    hc, scs = _scenarios(complexity, B, seed=10 + complexity, smooth=smooth, n_dyn=n_dyn, N_hor=N, num_steps_taken=taken)
     plan = FleetPlan.from_scenarios(scs, max_steps=steps)
     solver = gpu_solver_factory(workloads.solver_config_for(hc))
     fleet = pkg.NmpcFleet(solver, plan, log_steps=steps)
@@ -121,7 +142,7 @@ def test_fleet_steps_match_host_loop(oracle, gpu_solver_factory, complexity, B, 
         assert np.array_equal(st["idx"][ids], h["idx"][ids])
         assert np.array_equal(st["done"], h["done"])
     lg, n = fleet.log()
-    assert np.array_equal(n, st["t"])
+    assert np.array_equal(np.minimum(n, steps), np.minimum(st["t"], steps))   # the log holds `steps` plant steps
     b = 0
     assert np.array_equal(lg[b, :n[b], 0:3], np.array(scs[b].states[3:]).reshape(-1, 3)[:n[b]])
     fleet.close()

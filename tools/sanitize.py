@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """tools/sanitize.py — a small mixed workload for compute-sanitizer (memcheck / racecheck / synccheck / initcheck):
     compute-sanitizer --tool memcheck python tools/sanitize.py
-small batches (helper warps active), N=20 and N=40, plus a few fleet steps."""
+small batches (first wave and queue, obstacle slow paths), N=20 and N=40, plus a few fleet steps."""
 import os
 import sys
 
