@@ -37,7 +37,8 @@
 #define PROBE_BUCKETS 1024
 #define MEMP1 (NMPC_LBFGS_MAX + 1)
 #ifndef NMPC_SEG_UNR
-#define NMPC_SEG_UNR 2  // reference segments per trip of the cross-track loop (x S steps per lane in flight)
+#define NMPC_SEG_UNR 1  // reference segments per half-trip of the cross-track loop (x S steps per lane in flight); 2 is
+                        // as fast per segment but 110 instructions longer: -3 % at saturation (instruction cache)
 #endif
 
 // OpEn PANOC constants (panoc_engine.rs) — see oracle/nmpc_oracle.c for the restatement notes
@@ -152,6 +153,22 @@ __device__ __forceinline__ void sts1(uint32_t a, double v) { asm volatile("st.sh
 __device__ __forceinline__ void sts2(uint32_t a, double2 v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
 }
+__device__ __forceinline__ void sts2_if(uint32_t a, double2 v, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p st.shared.v2.f64 [%0], {%1, %2};\n\t}" ::"r"(a), "d"(v.x), "d"(v.y),
+                 "r"((int)on)
+                 : "memory");
+}
+// IEEE division / square root out of line: the hot loop holds one copy of the ~30-instruction sequences
+#ifndef NMPC_OOL_DIV
+#define NMPC_OOL_DIV 0  // measured: -2.4 % at saturation (the call costs more than the instruction-cache lines it saves)
+#endif
+#if NMPC_OOL_DIV
+__device__ __noinline__ double nm_div(double a, double b) { return a / b; }
+__device__ __noinline__ double nm_sqrt(double a) { return sqrt(a); }
+#else
+__device__ __forceinline__ double nm_div(double a, double b) { return a / b; }
+__device__ __forceinline__ double nm_sqrt(double a) { return sqrt(a); }
+#endif
 // one lane stores (predicated instruction, no divergent branch)
 __device__ __forceinline__ void sts1_if(uint32_t a, double v, bool on) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(a), "d"(v), "r"((int)on) : "memory");
@@ -377,15 +394,12 @@ struct Warp {
         for (int s = 0; s < S; s++) r[s] = lds2(la + k * vstride + 16u * G * s);
     }
     // stores come from ONE group (by default group 0; `from` = the group whose registers hold the vector)
-    // (warp barriers on both sides: the other groups may still be reading the vector's previous contents, and
-    //  they read the new ones next)
+    // (the callers place the warp barriers: one before a store to a vector that other groups may still be reading in
+    //  the same phase, one after the last store before anybody loads; phases are separated by barriers anyway)
     __device__ __forceinline__ void st(int k, const double2 (&r)[S], int from = 0) const {
-        __syncwarp();
-        if (grp == from) {
+        const bool mine = grp == from;
 #pragma unroll
-            for (int s = 0; s < S; s++) sts2(la + k * vstride + 16u * G * s, r[s]);
-        }
-        __syncwarp();
+        for (int s = 0; s < S; s++) sts2_if(la + k * vstride + 16u * G * s, r[s], mine);  // predicated: no branch
     }
 
     // unpack the parameter row (layout: include/nmpc_b200.h) into the arena
@@ -936,7 +950,7 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
     auto compute_fpr = [&](const double2(&u)[S], const double2(&uh)[S], double2(&fpr)[S]) -> double {
 #pragma unroll
         for (int s = 0; s < S; s++) fpr[s] = make_double2(u[s].x - uh[s].x, u[s].y - uh[s].y);
-        const double nf = sqrt(gsum<G>(dot(fpr, fpr)));
+        const double nf = nm_sqrt(gsum<G>(dot(fpr, fpr)));
         sput(H_NFPR, nf);
         return nf;
     };
@@ -999,6 +1013,7 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
     };
     // update_no_linesearch() of iteration 0: u <- u_half with the cost and gradient group 0 has just evaluated there
     auto first_iteration_update = [&](double cost_half) {
+        __syncwarp();
         W.st(V_GRAD, g);  // group 0 evaluated u_half
         __syncwarp();
         double2 u[S], gr[S], gs[S], uh[S];
@@ -1136,19 +1151,20 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                     tmp = (tmp >= mem1) ? tmp - mem1 : tmp;
                     W.st(V_S + tmp, sv);
                     W.st(V_Y + tmp, yv);
-                    const double rho_new = 1.0 / ys;
+                    const double rho_new = nm_div(1.0, ys);
                     bool accept = !(ss <= DBL_EPS || ys <= SY_EPSILON);
                     if (accept) {
                         // sqrt(<fpr, fpr>) is norm_fpr: same vector, same expression, same reduction order
-                        const double lhs = ys / ss, rhsb = CBFGS_EPSILON * norm_fpr;
+                        const double lhs = nm_div(ys, ss), rhsb = CBFGS_EPSILON * norm_fpr;
                         accept = (lhs > rhsb && isfinite(lhs) && isfinite(rhsb));
                     }
                     if (accept) {
+                        __syncwarp();  // the other groups have read the old (state, fpr) pair above
                         W.st(V_OLDS, u);
                         W.st(V_OLDG, fpr);
                         sts1_if(W.a_rho() + 8u * tmp, rho_new, lane == 0);
                         lb_head = tmp;  // rotate_right(1): the staging slot becomes slot 0
-                        sput(H_LBG, (1.0 / rho_new) / yy);
+                        sput(H_LBG, nm_div(nm_div(1.0, rho_new), yy));
                         lb_active = (lb_active + 1 < mem) ? lb_active + 1 : mem;
                     }
                 }
