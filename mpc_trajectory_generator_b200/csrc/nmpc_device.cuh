@@ -85,7 +85,7 @@ enum { I_NCOST = 0, I_NGRAD, I_ALM, I_INNER, I_NOUTER, I_STATUS, I_ISTATUS, I_IT
 #define ELL_STRIDE 6   // ex ey | cosA sinA | 1/rx^2 1/ry^2
 
 struct Lay {
-    int vlen, seg, circ, ell, ebd, rho, alpha, hdr, vref, total;
+    int vlen, seg, circ, ell, ebd, rho, alpha, syd, hdr, vref, total;
 };
 __host__ __device__ inline int even_up(int x) { return (x + 1) & ~1; }
 __host__ __device__ inline Lay make_layout(int N, int Nobs, int Nd) {
@@ -100,6 +100,7 @@ __host__ __device__ inline Lay make_layout(int N, int Nobs, int Nd) {
     L.ebd = o; o += 4 * Nd;  // per dynamic obstacle: centre and squared radius of a disc around all its poses
     L.rho = o; o += 12;
     L.alpha = o; o += 12;
+    L.syd = o; o += 12;  // Gram entries <s_p, y_(pair accepted after p)> by slot (paired two-loop recursion)
     L.hdr = o; o += H_COUNT;
     L.vref = o; o += even_up(G * S);
     L.total = o;
@@ -284,6 +285,20 @@ __device__ __forceinline__ void gsum4(double& a, double& b, double& c, double& d
         d = d + yd;
     }
 }
+template <int G>
+__device__ __forceinline__ void gsum5(double& a, double& b, double& c, double& d, double& e) {
+#pragma unroll
+    for (int off = G / 2; off; off >>= 1) {
+        const double ya = __shfl_xor_sync(FULL, a, off), yb = __shfl_xor_sync(FULL, b, off);
+        const double yc = __shfl_xor_sync(FULL, c, off), yd = __shfl_xor_sync(FULL, d, off);
+        const double ye = __shfl_xor_sync(FULL, e, off);
+        a = a + ya;
+        b = b + yb;
+        c = c + yc;
+        d = d + yd;
+        e = e + ye;
+    }
+}
 // Kogge-Stone inclusive scan of the lane totals over the group; returns the EXCLUSIVE prefix of this lane
 // (the scanned total of lane gl-1; 0.0 for the first lane)
 template <int G>
@@ -359,7 +374,7 @@ struct Warp {
     uint32_t la;       // sb + 16*gl : this lane's element of slot row 0 inside vector 0
     uint32_t vstride;  // bytes per vector
     uint32_t a_hdr;
-    int o_seg, o_circ, o_ell, o_ebd, o_rho, o_alpha, o_vref;  // byte offsets inside the arena (the same for every warp)
+    int o_seg, o_circ, o_ell, o_ebd, o_rho, o_alpha, o_syd, o_vref;  // byte offsets inside the arena (the same for every warp)
     int lane, grp, gl, N;
     __device__ __forceinline__ uint32_t a_seg() const { return sb + o_seg; }
     __device__ __forceinline__ uint32_t a_circ() const { return sb + o_circ; }
@@ -367,6 +382,7 @@ struct Warp {
     __device__ __forceinline__ uint32_t a_ebd() const { return sb + o_ebd; }
     __device__ __forceinline__ uint32_t a_rho() const { return sb + o_rho; }
     __device__ __forceinline__ uint32_t a_alpha() const { return sb + o_alpha; }
+    __device__ __forceinline__ uint32_t a_syd() const { return sb + o_syd; }
     __device__ __forceinline__ uint32_t a_vref() const { return sb + o_vref; }
     __device__ __forceinline__ int tix(int s) const { return S * gl + s; }
     __device__ __forceinline__ bool act(int s) const { return S * gl + s < N; }
@@ -384,7 +400,7 @@ struct Warp {
         la = sb + 16u * gl;
         vstride = (uint32_t)L.vlen * 8u;
         o_seg = L.seg * 8; o_circ = L.circ * 8; o_ell = L.ell * 8; o_ebd = L.ebd * 8; o_rho = L.rho * 8;
-        o_alpha = L.alpha * 8; o_vref = L.vref * 8;
+        o_alpha = L.alpha * 8; o_syd = L.syd * 8; o_vref = L.vref * 8;
         a_hdr = sb + L.hdr * 8u;
     }
     __device__ __forceinline__ double hdr(int i) const { return lds1(a_hdr + 8u * i); }
@@ -638,13 +654,14 @@ struct Warp {
                     for (int q = 0; q < 4; q++) {
                         const double2 cxy = lds2(ac + 32u * q);
                         const double r2 = lds1(ac + 32u * q + 16u);  // the slot behind the last circle holds r^2 = -1
-                        bool in = false;
+                        // (bitwise | and &: a short-circuit || would make every test wait for the one before)
+                        unsigned in = 0u;
 #pragma unroll
                         for (int s = 0; s < S; s++) {
                             const double dx = X[s] - cxy.x, dy = Y[s] - cxy.y;
-                            in = in || (act(s) && fma(-dy, dy, fma(-dx, dx, r2)) > 0.0);
+                            in |= (unsigned)(fma(-dy, dy, fma(-dx, dx, r2)) > 0.0) & (unsigned)act(s);
                         }
-                        mine |= in ? (1u << (k + q)) : 0u;
+                        mine |= in << (k + q);
                     }
                 }
                 unsigned todo = __reduce_or_sync(FULL, mine);
@@ -678,19 +695,27 @@ struct Warp {
                 }
             }
             const int Nd = cfg.Ndynobs;
+            unsigned near = 0u;  // dynamic obstacles (32 per round) whose bounding disc holds one of this lane's points
 #pragma unroll 1
-            for (int k = 0; k < Nd; k++) {
-                {   // nobody inside the disc around all poses of this obstacle: it adds exact zeros
-                    const double2 bxy = lds2(a_ebd() + 32u * k);
-                    const double R2 = lds1(a_ebd() + 32u * k + 16u);
-                    bool near = false;
+            for (int kb = 0; kb < Nd; kb += 32) {
+            const int kn = min(32, Nd - kb);
+            near = 0u;
+#pragma unroll 1
+            for (int k = 0; k < kn; k++) {
+                const double2 bxy = lds2(a_ebd() + 32u * (kb + k));
+                const double R2 = lds1(a_ebd() + 32u * (kb + k) + 16u);
+                unsigned in = 0u;
 #pragma unroll
-                    for (int s = 0; s < S; s++) {
-                        const double dx = X[s] - bxy.x, dy = Y[s] - bxy.y;
-                        near = near || (act(s) && fma(dx, dx, dy * dy) < R2);
-                    }
-                    if (!__any_sync(FULL, near)) continue;
+                for (int s = 0; s < S; s++) {
+                    const double dx = X[s] - bxy.x, dy = Y[s] - bxy.y;
+                    in |= (unsigned)(fma(dx, dx, dy * dy) < R2) & (unsigned)act(s);
                 }
+                near |= in << k;
+            }
+            unsigned todo_e = __reduce_or_sync(FULL, near);  // nobody near: the obstacle adds exact zeros
+            while (todo_e) {
+                const int k = kb + __ffs(todo_e) - 1;
+                todo_e &= todo_e - 1;
                 double hp[S], ta[S], tb[S], eca[S], esa[S];
                 bool any = false;
 #pragma unroll
@@ -703,9 +728,9 @@ struct Warp {
                     const double ea = fma(dx, csa.x, dy * csa.y);
                     const double eb = fma(dx, csa.y, -(dy * csa.x));
                     const double hh = fma(-(eb * eb), ir.y, fma(-(ea * ea), ir.x, 1.0));
-                    const bool in = act(s) && hh > 0.0;
+                    const bool in = act(s) & (hh > 0.0);
                     hp[s] = in ? hh : 0.0;
-                    any = any || in;
+                    any = any | in;
                     ta[s] = ea * ir.x;
                     tb[s] = eb * ir.y;
                 }
@@ -726,6 +751,7 @@ struct Warp {
                             gY[s] = fma(cg, hY, gY[s]);
                         }
                 }
+            }
             }
         }
         pen_out = pen;
@@ -1143,8 +1169,11 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                         sv[s] = make_double2(u[s].x - os[s].x, u[s].y - os[s].y);
                         yv[s] = make_double2(fpr[s].x - og[s].x, fpr[s].y - og[s].y);
                     }
-                    double ys = dot(sv, yv), ss = dot(sv, sv), yy = dot(yv, yv), ip = dot(gr, fpr);
-                    gsum4<G>(ip, ys, ss, yy);
+                    // ... and <s_newest, y_new>, the Gram entry the paired two-loop recursion needs (below)
+                    double2 sp[S];
+                    W.ld(V_S + lb_head, sp);
+                    double ys = dot(sv, yv), ss = dot(sv, sv), yy = dot(yv, yv), ip = dot(gr, fpr), sy1 = dot(sp, yv);
+                    gsum5<G>(ip, ys, ss, yy, sy1);
                     sput(H_IP, ip);
                     // lbfgs update_hessian(g = fpr, state = u)
                     int tmp = lb_head + mem;
@@ -1163,6 +1192,7 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                         W.st(V_OLDS, u);
                         W.st(V_OLDG, fpr);
                         sts1_if(W.a_rho() + 8u * tmp, rho_new, lane == 0);
+                        sts1_if(W.a_syd() + 8u * lb_head, sy1, lane == 0 && lb_active > 0);
                         lb_head = tmp;  // rotate_right(1): the staging slot becomes slot 0
                         sput(H_LBG, nm_div(nm_div(1.0, rho_new), yy));
                         lb_active = (lb_active + 1 < mem) ? lb_active + 1 : mem;
@@ -1185,57 +1215,54 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
 #pragma unroll
                 for (int s = 0; s < S; s++) q[s] = fpr[s];
                 if (lb_active > 0) {
-                    // alpha_k = rho_k <s_k, q>; q -= alpha_k y_k  (k = 0 newest).  The pair of the NEXT step is fetched
-                    // while this step's group sum is in flight; two steps per trip so the prefetch needs no moves.
+                    // The recursion alpha_k = rho_k <s_k, q>; q -= alpha_k y_k (k = 0 newest) taken TWO pairs at a time:
+                    //   alpha_{k+1} = rho_{k+1} ( <s_{k+1}, q> - alpha_k <s_{k+1}, y_k> )
+                    // so both inner products of a trip use the same q (ONE interleaved group sum instead of two
+                    // dependent ones) and <s_{k+1}, y_k> is the stored Gram entry syd[slot k+1].  Same for the
+                    // backward loop with <y_{k-1}, s_k> = syd[slot k].  (oracle: lb_apply, contract build)
                     const uint32_t a_s0 = W.la + V_S * W.vstride, a_y0 = W.la + V_Y * W.vstride;
                     auto ldv = [&](uint32_t base, int sl, double2(&r)[S]) {
 #pragma unroll
                         for (int s = 0; s < S; s++) r[s] = lds2(base + sl * W.vstride + 16u * G * s);
                     };
-                    auto fwd = [&](int k, const double2(&sv)[S], const double2(&yv)[S], double rho) {
-                        const double al = rho * gsum<G>(dot(sv, q));
-                        sts1_if(W.a_alpha() + 8u * k, al, lane == 0);
-#pragma unroll
-                        for (int s = 0; s < S; s++) {
-                            q[s].x = fma(-al, yv[s].x, q[s].x);
-                            q[s].y = fma(-al, yv[s].y, q[s].y);
-                        }
-                    };
-                    auto bwd = [&](int k, const double2(&sv)[S], const double2(&yv)[S], double rho) {
-                        const double alk = lds1(W.a_alpha() + 8u * k);
-                        const double beta = rho * gsum<G>(dot(yv, q));
-                        const double co = alk - beta;
-#pragma unroll
-                        for (int s = 0; s < S; s++) {
-                            q[s].x = fma(co, sv[s].x, q[s].x);
-                            q[s].y = fma(co, sv[s].y, q[s].y);
-                        }
-                    };
+                    auto nxt = [&](int sl) { return (sl + 1 >= mem1) ? 0 : sl + 1; };
+                    auto prv = [&](int sl) { return (sl == 0) ? mem1 - 1 : sl - 1; };
                     double2 sa[S], ya[S], sb[S], yb[S];
-                    double rhoa, rhob = 0.0;
-                    int sl = lb_head;  // physical slot of pair k; k + 1 is the next slot of the ring
+                    int sl = lb_head;  // physical slot of pair k; k + 1 (older) is the next slot of the ring
                     ldv(a_s0, sl, sa);
                     ldv(a_y0, sl, ya);
-                    rhoa = lds1(W.a_rho() + 8u * sl);
+                    double rhoa = lds1(W.a_rho() + 8u * sl);
                     int k = 0;
 #pragma unroll 1
                     for (; k + 1 < lb_active; k += 2) {
-                        sl = (sl + 1 >= mem1) ? 0 : sl + 1;
-                        ldv(a_s0, sl, sb);
-                        ldv(a_y0, sl, yb);
-                        rhob = lds1(W.a_rho() + 8u * sl);
-                        fwd(k, sa, ya, rhoa);
-                        sl = (sl + 1 >= mem1) ? 0 : sl + 1;
-                        ldv(a_s0, sl, sa);  // (one pair past the end on the last trip: a valid slot, never used)
+                        const int sl1 = nxt(sl);
+                        ldv(a_s0, sl1, sb);
+                        ldv(a_y0, sl1, yb);
+                        const double rhob = lds1(W.a_rho() + 8u * sl1), g1 = lds1(W.a_syd() + 8u * sl1);
+                        double pa = dot(sa, q), pb = dot(sb, q);
+                        gsum2<G>(pa, pb);
+                        const double al0 = rhoa * pa;
+                        const double al1 = rhob * fma(-al0, g1, pb);
+                        sts1_if(W.a_alpha() + 8u * k, al0, lane == 0);
+                        sts1_if(W.a_alpha() + 8u * k + 8u, al1, lane == 0);
+#pragma unroll
+                        for (int s = 0; s < S; s++) {
+                            q[s].x = fma(-al1, yb[s].x, fma(-al0, ya[s].x, q[s].x));
+                            q[s].y = fma(-al1, yb[s].y, fma(-al0, ya[s].y, q[s].y));
+                        }
+                        sl = nxt(sl1);
+                        ldv(a_s0, sl, sa);  // next trip's first pair (past the end on the last trip: a valid slot, unused)
                         ldv(a_y0, sl, ya);
                         rhoa = lds1(W.a_rho() + 8u * sl);
-                        fwd(k + 1, sb, yb, rhob);
                     }
-                    if (k < lb_active) {  // odd count: pair k is in (sa, ya)
-                        fwd(k, sa, ya, rhoa);
-                        k++;
-                    } else {  // even count: (sa, ya) hold the pair past the end; the newest processed pair is (sb, yb)
-                        sl = (sl == 0) ? mem1 - 1 : sl - 1;
+                    if (k < lb_active) {  // odd count: the oldest pair on its own
+                        const double al = rhoa * gsum<G>(dot(sa, q));
+                        sts1_if(W.a_alpha() + 8u * k, al, lane == 0);
+#pragma unroll
+                        for (int s = 0; s < S; s++) {
+                            q[s].x = fma(-al, ya[s].x, q[s].x);
+                            q[s].y = fma(-al, ya[s].y, q[s].y);
+                        }
                     }
                     __syncwarp();
                     const double lb_gamma = sget(H_LBG);
@@ -1244,25 +1271,43 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                         q[s].x = q[s].x * lb_gamma;
                         q[s].y = q[s].y * lb_gamma;
                     }
-                    // backward: k = lb_active-1 .. 0, sl = slot of pair lb_active-1
+                    // backward: pairs (k, k-1) from the oldest, k = lb_active-1
+                    k = lb_active - 1;
+                    sl = lb_head + k;
+                    sl = (sl >= mem1) ? sl - mem1 : sl;
                     ldv(a_s0, sl, sa);
                     ldv(a_y0, sl, ya);
                     rhoa = lds1(W.a_rho() + 8u * sl);
-                    k = lb_active - 1;
 #pragma unroll 1
                     for (; k >= 1; k -= 2) {
-                        sl = (sl == 0) ? mem1 - 1 : sl - 1;
-                        ldv(a_s0, sl, sb);
-                        ldv(a_y0, sl, yb);
-                        rhob = lds1(W.a_rho() + 8u * sl);
-                        bwd(k, sa, ya, rhoa);
-                        sl = (sl == 0) ? mem1 - 1 : sl - 1;
+                        const int sl1 = prv(sl);
+                        ldv(a_s0, sl1, sb);
+                        ldv(a_y0, sl1, yb);
+                        const double rhob = lds1(W.a_rho() + 8u * sl1), g1 = lds1(W.a_syd() + 8u * sl);
+                        const double alk = lds1(W.a_alpha() + 8u * k), alk1 = lds1(W.a_alpha() + 8u * k - 8u);
+                        double qa = dot(ya, q), qb = dot(yb, q);
+                        gsum2<G>(qa, qb);
+                        const double c0 = alk - rhoa * qa;
+                        const double c1 = alk1 - rhob * fma(c0, g1, qb);
+#pragma unroll
+                        for (int s = 0; s < S; s++) {
+                            q[s].x = fma(c1, sb[s].x, fma(c0, sa[s].x, q[s].x));
+                            q[s].y = fma(c1, sb[s].y, fma(c0, sa[s].y, q[s].y));
+                        }
+                        sl = prv(sl1);
                         ldv(a_s0, sl, sa);
                         ldv(a_y0, sl, ya);
                         rhoa = lds1(W.a_rho() + 8u * sl);
-                        bwd(k - 1, sb, yb, rhob);
                     }
-                    if (k == 0) bwd(0, sa, ya, rhoa);
+                    if (k == 0) {  // odd count: the newest pair on its own
+                        const double alk = lds1(W.a_alpha());
+                        const double co = alk - rhoa * gsum<G>(dot(ya, q));
+#pragma unroll
+                        for (int s = 0; s < S; s++) {
+                            q[s].x = fma(co, sa[s].x, q[s].x);
+                            q[s].y = fma(co, sa[s].y, q[s].y);
+                        }
+                    }
                 }
                 W.st(V_DIR, q);
                 __syncwarp();

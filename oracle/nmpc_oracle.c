@@ -532,6 +532,7 @@ typedef struct {
     double lgamma;
     double s[MEMP1][2 * MAXT], y[MEMP1][2 * MAXT];
     double rho[MEMP1], alpha[NMPC_LBFGS_MAX];
+    double syd[MEMP1]; /* by physical slot p: <s_p, y_q> with q the pair accepted right after p (contract build) */
     double old_state[2 * MAXT], old_g[2 * MAXT];
 } lbfgs_t;
 
@@ -560,15 +561,31 @@ static void lb_update(lbfgs_t* L, const double* g, const double* state) {
     memcpy(L->old_state, state, n2 * sizeof(double));
     memcpy(L->old_g, g, n2 * sizeof(double));
     double yy = vdot(L->S, y, y);
+    if (L->active > 0) { /* Gram entry of the pair that was the newest so far against the new one (see lb_apply) */
+        int prev = lb_slot(L, 0);
+        L->syd[prev] = vdot(L->S, L->s[prev], y);
+    }
     L->head = (L->head + L->mem) % (L->mem + 1); /* rotate_right(1): staging slot becomes slot 0 */
     L->lgamma = (1.0 / L->rho[tmp]) / yy;
     L->active = (L->active + 1 < L->mem) ? L->active + 1 : L->mem;
 }
 
-/* literal two-loop recursion of the lbfgs crate (Lbfgs::apply_hessian): 2*active sequential reductions */
+/* Two-loop recursion of the lbfgs crate (Lbfgs::apply_hessian).
+ *
+ * Serial build: the literal recursion — 2*active sequential reductions.
+ *
+ * Contract build (shared with the CUDA kernel): the same recursion taken TWO steps at a time.  For consecutive
+ * pairs k (newer) and k+1 of the forward loop
+ *     alpha_k     = rho_k     <s_k, q>
+ *     alpha_{k+1} = rho_{k+1} <s_{k+1}, q - alpha_k y_k> = rho_{k+1} ( <s_{k+1}, q> - alpha_k <s_{k+1}, y_k> ),
+ * so both inner products are taken against the SAME q (one interleaved warp reduction instead of two dependent
+ * ones) and <s_{k+1}, y_k> is a Gram entry that only changes when a pair is accepted (syd[], one extra inner
+ * product per update).  The backward loop pairs k and k-1 the same way with <y_{k-1}, s_k> = syd[slot k].
+ * Algebraically identical to the literal recursion; it differs in rounding only. */
 static void lb_apply(lbfgs_t* L, double* q) {
     const int n2 = L->n2;
     if (L->active == 0) return; /* empty buffer: H = I */
+#ifdef NMPC_ORACLE_SERIAL
     for (int k = 0; k < L->active; k++) {
         int sl = lb_slot(L, k);
         double al = L->rho[sl] * vdot(L->S, L->s[sl], q);
@@ -582,6 +599,40 @@ static void lb_apply(lbfgs_t* L, double* q) {
         double co = L->alpha[k] - beta;
         for (int i = 0; i < n2; i++) q[i] = FMA(co, L->s[sl][i], q[i]);
     }
+#else
+    const int m = L->active;
+    int k = 0;
+    for (; k + 1 < m; k += 2) {
+        int s0 = lb_slot(L, k), s1 = lb_slot(L, k + 1);
+        double pa = vdot(L->S, L->s[s0], q), pb = vdot(L->S, L->s[s1], q);
+        double al0 = L->rho[s0] * pa;
+        double al1 = L->rho[s1] * fma(-al0, L->syd[s1], pb);
+        L->alpha[k] = al0;
+        L->alpha[k + 1] = al1;
+        for (int i = 0; i < n2; i++) q[i] = fma(-al1, L->y[s1][i], fma(-al0, L->y[s0][i], q[i]));
+    }
+    if (k < m) {
+        int sl = lb_slot(L, k);
+        double al = L->rho[sl] * vdot(L->S, L->s[sl], q);
+        L->alpha[k] = al;
+        for (int i = 0; i < n2; i++) q[i] = fma(-al, L->y[sl][i], q[i]);
+    }
+    for (int i = 0; i < n2; i++) q[i] = q[i] * L->lgamma;
+    k = m - 1;
+    for (; k >= 1; k -= 2) {
+        int s0 = lb_slot(L, k), s1 = lb_slot(L, k - 1);
+        double qa = vdot(L->S, L->y[s0], q), qb = vdot(L->S, L->y[s1], q);
+        double c0 = L->alpha[k] - L->rho[s0] * qa;
+        double c1 = L->alpha[k - 1] - L->rho[s1] * fma(c0, L->syd[s0], qb);
+        for (int i = 0; i < n2; i++) q[i] = fma(c1, L->s[s1][i], fma(c0, L->s[s0][i], q[i]));
+    }
+    if (k == 0) {
+        int sl = lb_slot(L, 0);
+        double beta = L->rho[sl] * vdot(L->S, L->y[sl], q);
+        double co = L->alpha[0] - beta;
+        for (int i = 0; i < n2; i++) q[i] = fma(co, L->s[sl][i], q[i]);
+    }
+#endif
 }
 
 /* ------------------------------------------------------------------------- */
