@@ -528,7 +528,7 @@ struct Warp {
         double cth[S];
 #pragma unroll
         for (int s = 0; s < S; s++) {
-            const double v = act(s) ? ts * uv[s].y : 0.0;
+            const double v = ts * uv[s].y;  // padded steps hold (0, 0): no mask needed
             cth[s] = (s == 0) ? v : cth[s - 1] + v;
         }
         const double Eth = gscan_up_excl<G>(cth[S - 1], gl);
@@ -545,8 +545,8 @@ struct Warp {
             double ca[S], cb[S];
 #pragma unroll
             for (int s = 0; s < S; s++) {
-                const double va = act(s) ? ts * (uv[s].x * cs[s]) : 0.0;
-                const double vb = act(s) ? ts * (uv[s].x * sn[s]) : 0.0;
+                const double va = ts * (uv[s].x * cs[s]);  // padded steps: v = 0
+                const double vb = ts * (uv[s].x * sn[s]);
                 ca[s] = (s == 0) ? va : ca[s - 1] + va;
                 cb[s] = (s == 0) ? vb : cb[s - 1] + vb;
             }
@@ -1155,6 +1155,10 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                 // The update and the direction are computed BEFORE psi(u_half) is known: if the Lipschitz test then
                 // fails (rare), lip_halve() drops the memory exactly like the reference does before its update.
                 double2 q[S];
+                // rho and the initial scaling of a pair accepted in THIS iteration go to the recursion in registers;
+                // their stores (and the divisions behind them) stay off the recursion's critical path
+                bool fresh = false;
+                double rho_fresh = 0.0, lbg_fresh = 0.0;
                 if (flags & F_LBFIRST) {
                     sput(H_IP, gsum<G>(dot(gr, fpr)));
                     flags &= ~F_LBFIRST;
@@ -1191,15 +1195,20 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                         __syncwarp();  // the other groups have read the old (state, fpr) pair above
                         W.st(V_OLDS, u);
                         W.st(V_OLDG, fpr);
-                        sts1_if(W.a_rho() + 8u * tmp, rho_new, lane == 0);
                         sts1_if(W.a_syd() + 8u * lb_head, sy1, lane == 0 && lb_active > 0);
                         lb_head = tmp;  // rotate_right(1): the staging slot becomes slot 0
-                        sput(H_LBG, nm_div(nm_div(1.0, rho_new), yy));
+                        fresh = true;
+                        rho_fresh = rho_new;
+                        lbg_fresh = nm_div(nm_div(1.0, rho_new), yy);
                         lb_active = (lb_active + 1 < mem) ? lb_active + 1 : mem;
                     }
                 }
                 __syncwarp();
                 if (__builtin_expect(iteration == 0, 0)) {
+                    if (fresh) {  // (cannot happen at iteration 0: the first update only remembers the pair)
+                        sts1_if(W.a_rho() + 8u * lb_head, rho_fresh, lane == 0);
+                        sput(H_LBG, lbg_fresh);
+                    }
                     // group 0: psi and grad psi at u_half (Lipschitz test, then update_no_linesearch);
                     // the other groups: psi(u) — u was perturbed by the Lipschitz estimate, its cost is stale
 #pragma unroll
@@ -1231,7 +1240,8 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                     int sl = lb_head;  // physical slot of pair k; k + 1 (older) is the next slot of the ring
                     ldv(a_s0, sl, sa);
                     ldv(a_y0, sl, ya);
-                    double rhoa = lds1(W.a_rho() + 8u * sl);
+                    double rhoa = fresh ? rho_fresh : lds1(W.a_rho() + 8u * sl);
+                    const double rho_newest = rhoa;
                     int k = 0;
 #pragma unroll 1
                     for (; k + 1 < lb_active; k += 2) {
@@ -1265,7 +1275,7 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                         }
                     }
                     __syncwarp();
-                    const double lb_gamma = sget(H_LBG);
+                    const double lb_gamma = fresh ? lbg_fresh : sget(H_LBG);
 #pragma unroll
                     for (int s = 0; s < S; s++) {
                         q[s].x = q[s].x * lb_gamma;
@@ -1277,13 +1287,13 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                     sl = (sl >= mem1) ? sl - mem1 : sl;
                     ldv(a_s0, sl, sa);
                     ldv(a_y0, sl, ya);
-                    rhoa = lds1(W.a_rho() + 8u * sl);
+                    rhoa = (sl == lb_head) ? rho_newest : lds1(W.a_rho() + 8u * sl);
 #pragma unroll 1
                     for (; k >= 1; k -= 2) {
                         const int sl1 = prv(sl);
                         ldv(a_s0, sl1, sb);
                         ldv(a_y0, sl1, yb);
-                        const double rhob = lds1(W.a_rho() + 8u * sl1), g1 = lds1(W.a_syd() + 8u * sl);
+                        const double rhob = (sl1 == lb_head) ? rho_newest : lds1(W.a_rho() + 8u * sl1), g1 = lds1(W.a_syd() + 8u * sl);
                         const double alk = lds1(W.a_alpha() + 8u * k), alk1 = lds1(W.a_alpha() + 8u * k - 8u);
                         double qa = dot(ya, q), qb = dot(yb, q);
                         gsum2<G>(qa, qb);
@@ -1297,7 +1307,7 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                         sl = prv(sl1);
                         ldv(a_s0, sl, sa);
                         ldv(a_y0, sl, ya);
-                        rhoa = lds1(W.a_rho() + 8u * sl);
+                        rhoa = (sl == lb_head) ? rho_newest : lds1(W.a_rho() + 8u * sl);
                     }
                     if (k == 0) {  // odd count: the newest pair on its own
                         const double alk = lds1(W.a_alpha());
@@ -1310,6 +1320,10 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                     }
                 }
                 W.st(V_DIR, q);
+                if (fresh) {
+                    sts1_if(W.a_rho() + 8u * lb_head, rho_fresh, lane == 0);
+                    sput(H_LBG, lbg_fresh);
+                }
                 __syncwarp();
 #ifdef NMPC_PROFILE
                 prof[4] += clock64() - tl0;

@@ -25,14 +25,16 @@ from .. import _build
 _ACTIVE = {"cfg": None, "device": 0}
 
 
-def configure(reference_config=None, solver_config=None, device=0):
+def configure(reference_config=None, solver_config=None, device=0, max_duration_micros=0):
     """Bind the module to a problem size: either the reference's config dotdict
-    (src/utils/config.py:52-72) or an explicit NmpcConfig."""
+    (src/utils/config.py:52-72) or an explicit NmpcConfig.  `max_duration_micros` > 0 turns on the solver's time
+    budget (the reference builds its solver with 500 000, src/mpc/mpc_generator.py:9,186); 0 = iteration caps only."""
     if solver_config is None:
         if reference_config is None:
             solver_config = NmpcConfig.default()
         else:
             solver_config = NmpcConfig.from_reference_config(reference_config)
+        solver_config.max_duration_micros = int(max_duration_micros)
     _ACTIVE["cfg"] = solver_config
     _ACTIVE["device"] = int(device)
     return solver_config

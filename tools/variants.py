@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""tools/variants.py — build and time tuning variants of the solve kernel (same sources, extra -D flags).
+"""tools/variants.py — build and time tuning variants of the solve kernel (same sources, extra -D flags:
+NMPC_WARPS, NMPC_SEG_UNR, NMPC_ICLAMP, NMPC_OOL_DIV, NMPC_PROFILE).
 
     python tools/variants.py build  name=FLAG1,FLAG2 ...     (CPU: nvcc cross-compiles; .so files go to tools/_build/)
     python tools/variants.py run    [--batch 4096] [--big 32768] name ...   (GPU box)
