@@ -455,6 +455,37 @@ def main():
             del bc
             sc.close()
 
+        # closed-loop fleet stepping entirely on the device: one nmpc_fleet per rank,
+        # 8 192 robots (256 distinct plans on map 11, tiled) x 10 receding-horizon steps after one warm-up step
+        from mpc_trajectory_generator_b200.fleet import FleetPlan, NmpcFleet
+        from mpc_trajectory_generator_b200.host import assembly as _asm
+        t_gen = time.perf_counter()
+        fhc = _asm.HostConfig.default()
+        fsteps, frobots, fdistinct = 10, 8192, 256
+        fplan = FleetPlan.from_scenarios(workloads.random_scenarios(fhc, 11, fdistinct, seed=5 + rank), max_steps=fsteps + 1)
+        ftile = lambda a_: np.ascontiguousarray(np.concatenate([a_] * (frobots // fdistinct)))  # noqa: E731
+        fbig = FleetPlan(ftile(fplan.n_ref), ftile(fplan.ref), ftile(fplan.n_vert), ftile(fplan.vert), ftile(fplan.start),
+                         ftile(fplan.goal), fplan.brake_vel, fplan.brake_dist, fplan.weights, fplan.base_speed,
+                         fplan.circle_radius)
+        gen_s = time.perf_counter() - t_gen
+        fsolver = pkg.NmpcSolver(workloads.solver_config_for(fhc), device=local_rank)
+        fleet = NmpcFleet(fsolver, fbig)
+        fleet.step(1)
+        sync_all()
+        fleet.step(fsteps)
+        fms = fsolver.last_kernel_ms          # device time of the fsteps steps (events on the handle's stream)
+        sync_all()
+        mx, per = over_ranks(fms)
+        fst = fleet.state()
+        extra.append({"config": "fleet", "workload": f"{frobots} robots per GPU ({fdistinct} distinct plans on map 11, tiled), "
+                      f"{fsteps} closed-loop steps in one nmpc_fleet_step call (assemble -> solve -> advance on the device)",
+                      "batch_per_gpu": frobots, "steps": fsteps, "scaling": "weak", "value": world * frobots * fsteps / (mx * 1e-3),
+                      "unit": "robot-steps/s", "ms_per_step": mx / fsteps, "kernel_ms_per_step_by_rank": [p_ / fsteps for p_ in per],
+                      "exit_status_counts": np.bincount(fst["status"], minlength=4).tolist(),
+                      "inner_iterations_mean": 0.0, "workload_generation_s": gen_s})
+        fleet.close()
+        fsolver.close()
+
     if rank == 0:
         peak, peak_src = load_peaks()
         abytes = algorithmic_bytes(N, Nobs, Nd)
