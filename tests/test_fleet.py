@@ -48,6 +48,22 @@ def test_plan_packing_cpu():
     assert plan.circle_radius == hc.vehicle_width / 2 + hc.vehicle_margin
 
 
+def test_no_circles_on_an_obstacle_free_map_cpu():
+    """The reference fills the static-circle slots only when the map has obstacles (src/path_generator.py:295), even
+    though find_original_vertices also returns corner vertices of a non-convex boundary: the fleet plan must not send
+    them either."""
+    hc = assembly.HostConfig.default()
+    gmap = {"complexity": 99, "boundary": [[0.0, 0.0], [20.0, 0.0], [20.0, 20.0], [12.0, 20.0], [12.0, 8.0], [8.0, 8.0],
+                                            [8.0, 20.0], [0.0, 20.0]],
+            "obstacles": [], "start": [4.0, 16.0, -1.5], "end": [16.0, 16.0, 1.5], "dyn_obs": []}
+    sc = assembly.Scenario(hc, gmap)
+    assert sc.ok and len(sc.path) >= 3 and len(sc.vert) > 0      # the path bends around boundary corners
+    plan = FleetPlan.from_scenarios([sc])
+    assert plan.n_vert[0] == 0
+    p = sc.parameters()
+    assert not np.any(p[20 + hc.N_hor:20 + hc.N_hor + 3 * hc.Nobs])   # the host mirror sends no circles either
+
+
 @pytest.mark.parametrize("steps,n_dyn", [(1, 3), (2, 3), (3, 3), (1, 1), (2, 2), (3, 1)])
 def test_dynamic_schedule_matches_ring_cpu(steps, n_dyn):
     """The closed form the device uses against the reference's rotate-and-append ring (src/path_generator.py:306-316,

@@ -117,9 +117,10 @@ def test_empty_and_single(oracle, gpu_solver_factory):
 
 
 def test_golden_reference_run_replay(gpu_solver_factory):
-    """BASELINE config 1: the parameter sequence recorded from the UNMODIFIED reference
-    PathGenerator.run (tests/golden/config1_run.npz) replayed through nmpc_call, whose handle
-    keeps (u, y) between calls like OpEn's TCP server; every reply must equal the recorded one."""
+    """BASELINE config 1: the parameter sequence the UNMODIFIED reference PathGenerator.run assembled while it was
+    driven by our oracle behind the manager (tests/golden/config1_run.npz: the parameters are the reference's, the
+    replies are the oracle's) replayed through nmpc_call, whose handle keeps (u, y) between calls like OpEn's TCP
+    server; every reply must equal the recorded one."""
     import os
     import mpc_trajectory_generator_b200 as pkg
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_run.npz"))
@@ -135,7 +136,7 @@ def test_golden_reference_run_replay(gpu_solver_factory):
 def test_manager_closed_loop_default_config():
     """The OptimizerTcpManager-shaped object drives a full receding-horizon run (our host mirror of
     src/path_generator.py:290-403) on map complexity=1 / configs/default.yaml and reaches the goal
-    exactly like the recorded reference run."""
+    exactly like the run recorded from the reference orchestrator with the oracle behind it."""
     import os
     from mpc_trajectory_generator_b200.host import assembly, opengen_compat
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_run.npz"))
