@@ -84,6 +84,16 @@
 #define Y_SET_BOUND 1e12              /* opengen SetYCalculator.LARGE_NUM */
 
 static int g_trace = 0; /* NMPC_ORACLE_TRACE, read once per batch call */
+/* NMPC_ORACLE_VARIANT (bit mask, read once per batch call; 0 = the restatement everything else is compared with).
+ * Each bit flips ONE behaviour that was restated from recollection of OpEn's source to what a reader of OpEn's
+ * documentation might expect instead; tools/sensitivity.py reports how far the iteration profile and the replies move
+ * (DESIGN.md §3).  Never set by the tests or the benchmark.
+ *   1  AKKT residual with the gradient of the PREVIOUS iterate (not the degenerate |gamma*fpr| / gamma)
+ *   2  exhausted line search falls back to u_half (not: keeps the last trial point)
+ *   4  the Lipschitz estimate restores u (not: leaves it perturbed by h)
+ *   8  ALM criterion 1 may hold in the first outer iteration (not: needs a second one)
+ *  16  the penalty parameter may grow after the first outer iteration (not: iteration 0 always counts as a stall) */
+static int g_variant = 0;
 
 /* ------------------------------------------------------------------------- */
 /* sincos: Cody-Waite reduction by pi/2 (three fma terms), fdlibm kernel
@@ -647,6 +657,7 @@ typedef struct {
     int n2, iteration;
     double gamma, inv_gamma, sigma, lip, cost, norm_fpr, tau, tol, akkt_tol;
     double grad[2 * MAXT], uhalf[2 * MAXT], fpr[2 * MAXT], dir[2 * MAXT], gstep[2 * MAXT], uplus[2 * MAXT];
+    double grad_prev[2 * MAXT]; /* variant 1 only */
     lbfgs_t lb;
 } panoc_t;
 
@@ -690,6 +701,9 @@ static void panoc_init(panoc_t* C, double* u) {
     for (int i = 0; i < n2; i++) u[i] = u[i] + hv[i];
     eval_psi(S, u, C->c, C->y, gh, 0, 0);
     C->lip = sqrt(vdiff2(S, gh, C->grad)) / norm_h;
+    if (g_variant & 4)
+        for (int i = 0; i < n2; i++) u[i] = u[i] - hv[i];
+    memset(C->grad_prev, 0, sizeof(C->grad_prev));
     set_gamma(C, GAMMA_L_COEFF / fmax(C->lip, MIN_L_ESTIMATE));
     C->sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * C->gamma);
     grad_step_half(C, u);
@@ -708,6 +722,7 @@ static int panoc_step(panoc_t* C, double* u) {
         for (int t = 0; t < N; t++) {
             double g0 = C->grad[2 * t], g1 = C->grad[2 * t + 1];
             double p0 = C->iteration ? g0 : 0.0, p1 = C->iteration ? g1 : 0.0;
+            if (g_variant & 1) { p0 = C->grad_prev[2 * t]; p1 = C->grad_prev[2 * t + 1]; }
 #ifdef NMPC_ORACLE_SERIAL
             double r0 = C->fpr[2 * t] / C->gamma + g0 - p0;
             double r1 = C->fpr[2 * t + 1] / C->gamma + g1 - p1;
@@ -737,6 +752,7 @@ static int panoc_step(panoc_t* C, double* u) {
         it++;
     }
     C->sigma = (1.0 - GAMMA_L_COEFF) / (4.0 * C->gamma);
+    if (g_variant & 1) memcpy(C->grad_prev, C->grad, n2 * sizeof(double));
     /* lbfgs_direction() */
     lb_update(&C->lb, C->fpr, u);
     if (C->iteration > 0) {
@@ -763,6 +779,14 @@ static int panoc_step(panoc_t* C, double* u) {
             if (!(lhs > rhs_ls && nls < MAX_LINESEARCH_ITERATIONS)) break;
             C->tau /= 2.0;
             nls++;
+        }
+        if ((g_variant & 2) && nls == MAX_LINESEARCH_ITERATIONS) {
+            /* fallback: u <- the current half step (the last trial's projected gradient step); cost / gradient there */
+            double tmpu[2 * MAXT];
+            memcpy(tmpu, C->uhalf, n2 * sizeof(double));
+            memcpy(C->uplus, tmpu, n2 * sizeof(double));
+            C->cost = eval_psi(S, C->uplus, C->c, C->y, C->grad, 0, 0);
+            grad_step_half(C, C->uplus);
         }
         memcpy(u, C->uplus, n2 * sizeof(double));
     }
@@ -860,12 +884,12 @@ static int solve_ws(workspace* W, const nmpc_config* cfg, const double* p, doubl
         double acc = 0.0;
         for (int k = 0; k < S->Nobs + S->Nd; k++) acc = FMA(F2[k], F2[k], acc);
         f2np = sqrt(acc);
-        int crit1 = iteration > 0 && dynp <= C->c * cfg->delta_tolerance + DBL_EPS;
+        int crit1 = (iteration > 0 || (g_variant & 8)) && dynp <= C->c * cfg->delta_tolerance + DBL_EPS;
         int crit2 = (S->Nobs + S->Nd == 0) || f2np <= cfg->delta_tolerance + DBL_EPS;
         int crit3 = C->akkt_tol <= cfg->tolerance + DBL_EPS;
         if (crit1 && crit2 && crit3) { done = 1; break; }
         int stall;
-        if (iteration == 0) stall = 1;
+        if (iteration == 0 && !(g_variant & 16)) stall = 1;
         else {
             int ca = dynp <= cfg->sufficient_decrease_coeff * dyn + DBL_EPS;
             int cp = f2np <= cfg->sufficient_decrease_coeff * f2n + DBL_EPS;
@@ -917,6 +941,7 @@ int nmpc_oracle_solve_batch(const nmpc_config* cfg, int32_t B, const double* Pm,
     const int np = nmpc_param_len(cfg), n2 = 2 * cfg->N_hor;
     int bad = 0;
     g_trace = getenv("NMPC_ORACLE_TRACE") != NULL;
+    g_variant = getenv("NMPC_ORACLE_VARIANT") ? atoi(getenv("NMPC_ORACLE_VARIANT")) : 0;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #pragma omp parallel
