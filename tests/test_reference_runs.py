@@ -93,3 +93,50 @@ def test_gpu_call_sequence_on_the_moving_obstacle_map(gpu_solver_factory, runs):
     i0 = np.nonzero((runs["map"] == 12) & (runs["step"] == 0))[0][0]
     u, st, stats, ms = s.call(runs["P"][i0])
     assert st == runs["status"][i0] and np.array_equal(u, runs["U"][i0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cx", list(range(1, 13)))
+def test_fleet_kernels_walk_the_recorded_runs(oracle, gpu_solver_factory, runs, cx):
+    """The reference's own run of map cx (its start / goal, its moving obstacles) stepped by the device fleet kernels
+    (assemble -> solve with the persisted warm start -> plant step, all on the device): over the first 19 steps the
+    device loop equals the host mirror + oracle loop bit for bit, and at every kept step of the recording (0, 3, ...,
+    18) the parameter vector assembled ON THE DEVICE, the reply and the exit flag are the recorded ones bit for bit —
+    the recording's vectors come from the unmodified src/path_generator.py:293-382 and its plant
+    (src/mpc/mpc_generator.py:225-231, libm sin / cos; the solver's sincos is <= 2 ulp away and happens to round the
+    same way along these steps; from step 21 of map 6 on the two drift apart at 1e-6, which is why this stops at 18)."""
+    import mpc_trajectory_generator_b200 as pkg
+    from mpc_trajectory_generator_b200 import workloads
+    from mpc_trajectory_generator_b200.fleet import FleetPlan
+    steps = 19
+    hc = assembly.HostConfig.default()
+    gmap = assembly.load_maps()[cx]
+    dev_sc = assembly.Scenario(hc, gmap, sinus_object=(cx == 12))
+    host_sc = assembly.Scenario(hc, gmap, sinus_object=(cx == 12))
+    plan = FleetPlan.from_scenarios([dev_sc], max_steps=steps)
+    solver = gpu_solver_factory(workloads.solver_config_for(hc))
+    fleet = pkg.NmpcFleet(solver, plan, log_steps=steps)
+    sel = np.nonzero(runs["map"] == cx)[0]
+    kept = {int(runs["step"][i]): i for i in sel}
+    ocfg = oracle.default_config()
+    U = np.zeros((1, 2 * hc.N_hor))
+    Y = np.zeros((1, 2 * hc.N_hor))
+    checked = 0
+    for k in range(steps):
+        fleet.step(1)
+        P, Ud, Yd = fleet.last()
+        st = fleet.state()
+        ph = host_sc.parameters()
+        assert np.array_equal(P[0], ph), f"map {cx} step {k}: device and host mirror assemble different parameters"
+        U, Y, sth, _ = oracle.solve_batch(ocfg, ph[None], U, Y)
+        assert st["status"][0] == sth[0] and np.array_equal(Ud[0], U[0]) and np.array_equal(Yd[0], Y[0])
+        if k in kept:
+            i = kept[k]
+            assert np.array_equal(P[0], runs["P"][i]), f"map {cx} step {k}: not the reference's parameter vector"
+            assert np.array_equal(Ud[0], runs["U"][i]) and st["status"][0] == runs["status"][i]
+            checked += 1
+        finished = host_sc.apply(U[0], sincos=lambda th: oracle.sincos(th))
+        assert np.array_equal(fleet.state()["state"][0], np.array(host_sc.states[-3:]))
+        assert not finished
+    assert checked == 7
+    fleet.close()
