@@ -1057,6 +1057,23 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
         phase = PH_STEP_DONE;
     };
 
+    // PANOCOptimizer::solve's loop condition after a step (inlined where a step ends: no trip through the phase switch)
+    auto step_done = [&]() {
+        if (!(flags & F_CONT)) {
+            phase = PH_SOLVE_END;
+            return;
+        }
+        const int num_iter = iget(I_NUMIT) + 1;
+        iput(I_NUMIT, num_iter);
+        if (!(num_iter < cfg.max_inner_iterations)) flags &= ~F_CONT;
+        if (out_of_time()) {  // PANOCOptimizer::solve: time ran out
+            flags |= F_TIMEOUT;
+            phase = PH_SOLVE_END;
+            return;
+        }
+        phase = PH_STEP_BEGIN;
+    };
+
 #ifdef NMPC_PROFILE
     long long last_t = clock64();
     int last_slot = -1;  // per-phase cycles outside the evaluations: slots 16+phase (pre), 32+phase (post)
@@ -1337,19 +1354,7 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                 break;
             }
             case PH_STEP_DONE: {
-                if (!(flags & F_CONT)) {
-                    phase = PH_SOLVE_END;
-                    continue;
-                }
-                const int num_iter = iget(I_NUMIT) + 1;
-                iput(I_NUMIT, num_iter);
-                if (!(num_iter < cfg.max_inner_iterations)) flags &= ~F_CONT;
-                if (out_of_time()) {  // PANOCOptimizer::solve: time ran out
-                    flags |= F_TIMEOUT;
-                    phase = PH_SOLVE_END;
-                    continue;
-                }
-                phase = PH_STEP_BEGIN;
+                step_done();
                 continue;
             }
             case PH_SOLVE_END: {
@@ -1490,7 +1495,7 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                     flags |= F_FBE;
                     __syncwarp();
                     iteration++;
-                    phase = PH_STEP_DONE;
+                    step_done();
                 } else {
                     e0 += NG - gfirst;
                     flags &= ~F_GFIRST;

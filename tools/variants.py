@@ -83,8 +83,18 @@ def cmd_one(name, batch, big, reps):
             np.save(ref, U)
             same = None
         else:
-            same = bool(np.array_equal(np.load(ref), U))
+            R = np.load(ref)
+            same = bool(np.array_equal(R, U, equal_nan=True))
+            if not same:
+                bad = np.nonzero(~np.all((R == U) | (np.isnan(R) & np.isnan(U)), axis=1))[0]
+                res[tag + "_mismatch_rows"] = [int(len(bad))] + [int(x) for x in bad[:8]]
         res[tag] = {"B": B, "ms": round(best, 3), "solves_per_s": round(B / best * 1e3, 1), "bit_exact_vs_base": same}
+    # one problem alone (the hardest of config 2): the latency that bounds the config-2 step
+    ms = []
+    for r in range(3):
+        _, _, st1, stats1 = s.solve_batch(P2[1207:1208])
+        ms.append(s.last_kernel_ms)
+    res["lone_ms"] = round(min(ms), 3)
     s.close()
     print(json.dumps(res), flush=True)
 
