@@ -78,7 +78,9 @@ enum { H_X0 = 0, H_Y0, H_TH0, H_VINIT, H_WINIT, H_XREF, H_YREF, H_THREF, H_Q, H_
        // PANOC scalars: every lane stores the same value and reads back its own store.  Keeping them (and the
        // counters below) here instead of in registers is what lets the evaluation have the register file
        H_GAMMA = 28, H_INVG, H_SIGMA, H_COST, H_NFPR, H_RHSLS, H_LBG, H_FBEU, H_IP, H_PENC, H_PINV, H_TBEG,
-       H_INTS = 40, H_COUNT = 48 };
+       H_INTS = 40,
+       H_HRES = 48,  // helper mode: (psi, left-hand side) of the trial each group evaluated, 2 doubles x NG
+       H_COUNT = 56 };
 enum { I_NCOST = 0, I_NGRAD, I_ALM, I_INNER, I_NOUTER, I_STATUS, I_ISTATUS, I_ITLIP, I_NUMIT, I_FLAGS };
 #define SEG_STRIDE 6   // s1x s1y | dx dy | inv pad
 #define CIRC_STRIDE 4  // cx cy | r2 (original slot index as int in the 4th double)
@@ -175,6 +177,50 @@ __device__ __forceinline__ void sts1_if(uint32_t a, double v, bool on) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(a), "d"(v), "r"((int)on) : "memory");
 }
 __device__ __forceinline__ void stsi(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// ---------------------------------------------------------------------------------
+// Helper warps.  A warp that has run out of problems attaches itself to a warp of its CTA that is still solving (the
+// "owner") and, every PANOC iteration, evaluates the owner's SECOND batch of line-search trials while the owner's own
+// call evaluates psi(u_half) and the first batch (solve_problem: PH_HELP / take_from_helper).  When the owner's call
+// accepts nothing (a fifth to half of the iterations) the next batch is already there.  Same operations on the same
+// inputs: the results do not depend on who evaluates a trial.  One mailbox per warp slot; flags move with
+// release / acquire at CTA scope.  Every wait is a loop that ALL lanes of the warp execute (one warp-wide load
+// returns one value, so the loop is warp-uniform): a polling loop run by lane 0 alone leaves the warp split in two
+// for everything that follows, at a third of the speed.
+struct Mailbox {
+    unsigned seq;     // owner: bumped after the trial inputs (V_U, V_FPR, V_DIR, step size) of an iteration are in place
+    unsigned done;    // owner's box: the seq whose results are in the helper's arena; helper's own box: the last seq it took
+    unsigned state;   // MB_RUNNING while the warp owns problems, MB_DONE once it has retired
+    unsigned helper;  // owner's box: 0, or 1 + the slot of the attached helper; helper's own box: the slot of its owner
+};
+struct HelpShared {
+    Mailbox mb[32];
+    unsigned arena_bytes, hdr_off, smem_base, pad;  // so that cold paths need no registers for them
+};
+__shared__ HelpShared g_help;
+enum { MB_RUNNING = 1, MB_DONE = 2 };
+enum { MB_SEQ = 0, MB_DONEQ = 4, MB_STATE = 8, MB_HELPER = 12 };  // byte offsets inside a mailbox
+enum { HELP_NONE = 0, HELP_OWNER = 1, HELP_HELPER = 2 };           // solve_problem's `help` argument
+__device__ __forceinline__ uint32_t help_base() { return (uint32_t)__cvta_generic_to_shared(&g_help); }
+__device__ __forceinline__ uint32_t mbox_of(int slot) { return help_base() + 16u * (uint32_t)slot; }
+__device__ __forceinline__ uint32_t help_u32(int field) { return ((const volatile unsigned*)&g_help.arena_bytes)[field]; }
+__device__ __forceinline__ unsigned ld_acquire(uint32_t a) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t a, unsigned v) { asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned cas_acq_rel(uint32_t a, unsigned cmp, unsigned val) {
+    unsigned old;
+    asm volatile("atom.acq_rel.cta.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+// a short pause between two polls of a flag (nanosleep's granularity is far too coarse here)
+__device__ __forceinline__ void spin_wait(int cycles) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < cycles) {
+    }
+}
 
 // Rectangle::project of OpEn is comparison-based: a NaN stays a NaN (and ends the solve as NotFinite)
 __device__ __forceinline__ double clampd(double x, double lo, double hi) { return (x < lo) ? lo : ((x > hi) ? hi : x); }
@@ -402,6 +448,12 @@ struct Warp {
         o_seg = L.seg * 8; o_circ = L.circ * 8; o_ell = L.ell * 8; o_ebd = L.ebd * 8; o_rho = L.rho * 8;
         o_alpha = L.alpha * 8; o_syd = L.syd * 8; o_vref = L.vref * 8;
         a_hdr = sb + L.hdr * 8u;
+    }
+    // point this view at the arena of warp slot `slot` (a helper warp looks at its owner's arena)
+    __device__ __forceinline__ void rebase(int slot) {
+        sb = help_u32(2) + (uint32_t)slot * help_u32(0);
+        la = sb + 16u * gl;
+        a_hdr = sb + help_u32(1);
     }
     __device__ __forceinline__ double hdr(int i) const { return lds1(a_hdr + 8u * i); }
     // vector k of the arena: every lane reads its S (v, w) pairs; all groups see the same vector
@@ -885,7 +937,7 @@ struct Warp {
 // ---------------------------------------------------------------------------------
 // The solver: ALM/PM outer loop around PANOC as a phase machine with one evaluation site.
 // Phases that end in an evaluation set x (per group) and fall through to it; the others `continue`.
-enum Phase { PH_OUTER_BEGIN, PH_INIT, PH_STEP_BEGIN, PH_A, PH_RETRY, PH_LS, PH_STEP_DONE, PH_SOLVE_END, PH_F2, PH_EXIT };
+enum Phase { PH_OUTER_BEGIN, PH_INIT, PH_STEP_BEGIN, PH_A, PH_RETRY, PH_LS, PH_STEP_DONE, PH_SOLVE_END, PH_F2, PH_EXIT, PH_HELP };
 
 __device__ __forceinline__ unsigned long long nm_globaltimer() {
     unsigned long long t;
@@ -893,11 +945,60 @@ __device__ __forceinline__ unsigned long long nm_globaltimer() {
     return t;
 }
 
+// Owner side of the helper scheme, out of line (it runs in a fraction of the iterations and must not cost the solver's
+// hot loop registers or instruction-cache lines): wait for the helper's results of this iteration's post, pick the first
+// of its NG trials that passes the line search (trial exponents NG-1 .. 2NG-2), copy that trial's (x, grad, gradient
+// step, half step) from the helper's arena over V_U, V_GRAD, V_GSTEP, V_UHALF and its (psi, lhs) into the header.
+// Returns the accepted trial's index 0 .. NG-1, -1 if none passes, -2 if the helper did not answer (never seen; then
+// the caller evaluates the batch itself).
+template <int G, int S>
+__device__ __noinline__ int take_from_helper(uint32_t la, uint32_t vstride, uint32_t a_hdr, int lane) {
+    constexpr int NG = 32 / G;
+    const uint32_t mbs = mbox_of((int)(threadIdx.x >> 5));
+    const unsigned want = ld_acquire(mbs + MB_SEQ);  // this warp's own last post
+    int polls = 0;
+    while (ld_acquire(mbs + MB_DONEQ) != want) {  // every lane polls (warp-uniform)
+        spin_wait(32);
+        if (++polls > (1 << 22)) return -2;
+    }
+    __syncwarp();
+    const int hw = (int)ld_acquire(mbs + MB_HELPER) - 1;
+    const uint32_t hsb = help_u32(2) + (uint32_t)hw * help_u32(0);  // the helper's arena
+    const uint32_t hhdr = hsb + help_u32(1) + 8u * H_HRES;
+    const double rhs = lds1(a_hdr + 8u * H_RHSLS);
+    int k = -1;
+#pragma unroll
+    for (int j = NG - 1; j >= 0; j--) {
+        const double lj = lds1(hhdr + 16u * j + 8u);
+        if (!(lj > rhs) || (NG - 1 + j) >= MAX_LINESEARCH_ITERATIONS) k = j;  // the first one wins
+    }
+    if (k < 0) return -1;
+    const int gl = lane % G;
+    const bool g0 = lane < G;  // group 0 stores (like Warp::st)
+    const uint32_t hla = hsb + 16u * gl + (uint32_t)(4 * k) * vstride;
+    const int dst[4] = {V_U, V_GRAD, V_GSTEP, V_UHALF};
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        double2 t[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) t[s] = lds2(hla + (uint32_t)v * vstride + 16u * G * s);
+#pragma unroll
+        for (int s = 0; s < S; s++) sts2_if(la + (uint32_t)dst[v] * vstride + 16u * G * s, t[s], g0);
+    }
+    sts1(a_hdr + 8u * H_COST, lds1(hhdr + 16u * k));
+    sts1(a_hdr + 8u * H_FBEU, lds1(hhdr + 16u * k + 8u));
+    __syncwarp();
+    return k;
+}
+
 // Solves the staged problem.  The decision vector lives in the arena (V_U: start point in, solution out) and the
 // multipliers in V_YL; the warp-uniform solver state lives in the arena header (H_GAMMA ..., I_*), so that across an
 // evaluation only a handful of registers stay live.
 template <int G, int S>
-__device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_out = nullptr) {
+// help: HELP_NONE, HELP_OWNER (the kernel has mailboxes: post the trial inputs once a helper is attached) or HELP_HELPER
+// (W views the OWNER's arena; this warp's own mailbox holds the owner's slot and the last seq taken; the call returns
+// when the owner retires).
+__device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_out = nullptr, int help = HELP_NONE) {
     constexpr int NG = 32 / G;
 #ifdef NMPC_PROFILE
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -911,6 +1012,7 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
     auto sput = [&](int i, double v) { sts1(W.a_hdr + 8u * i, v); };
     auto iget = [&](int i) { return ldsi(W.a_hdr + 8u * H_INTS + 4u * i); };
     auto iput = [&](int i, int v) { stsi(W.a_hdr + 8u * H_INTS + 4u * i, v); };
+    if (help != HELP_HELPER) {
     sput(H_AKKT, cfg.initial_tolerance);
     sput(H_F2N, 0.0);
     sput(H_DYN, 0.0);
@@ -922,12 +1024,14 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
     sput(H_PINV, 1.0 / fmax(cfg.initial_penalty, 1.0));
     iput(I_NCOST, 0); iput(I_NGRAD, 0); iput(I_ALM, 0); iput(I_INNER, 0); iput(I_NOUTER, 0);
     iput(I_STATUS, NMPC_CONVERGED); iput(I_ISTATUS, NMPC_CONVERGED); iput(I_ITLIP, 0); iput(I_NUMIT, 0);
+    }
     // the few values that stay in registers
     int iteration = 0, lb_active = 0, lb_head = 0, e0 = 0;
     // flags: 1 lb_first, 2 gfirst (group 0 of the current call evaluates u_half), 4 cont, 8 fbe_valid, 16 timed_out
-    enum { F_LBFIRST = 1, F_GFIRST = 2, F_CONT = 4, F_FBE = 8, F_TIMEOUT = 16 };
-    int flags = F_LBFIRST | F_CONT;
-    if (cfg.max_duration_micros > 0) sput(H_TBEG, __longlong_as_double((long long)nm_globaltimer()));
+    //        32 posted (a helper evaluates the second batch of trials of this iteration), 64 the kernel has mailboxes
+    enum { F_LBFIRST = 1, F_GFIRST = 2, F_CONT = 4, F_FBE = 8, F_TIMEOUT = 16, F_POSTED = 32, F_MBOX = 64 };
+    int flags = F_LBFIRST | F_CONT | (help == HELP_OWNER ? F_MBOX : 0);
+    if (help != HELP_HELPER && cfg.max_duration_micros > 0) sput(H_TBEG, __longlong_as_double((long long)nm_globaltimer()));
     auto out_of_time = [&]() -> bool {
         if (cfg.max_duration_micros <= 0) return false;
         const unsigned long long t0 = (unsigned long long)__double_as_longlong(sget(H_TBEG));
@@ -937,7 +1041,7 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
     double2 x[S], g[S];  // this group's evaluation point / gradient out
     double pen = 0.0;
     bool zero_c = false;
-    int phase = PH_OUTER_BEGIN;
+    int phase = (help == HELP_HELPER) ? PH_HELP : PH_OUTER_BEGIN;
 
     auto set_gamma = [&](double gm) {  // sigma only changes with gamma: computed here, not once per iteration
         sput(H_GAMMA, gm);
@@ -989,7 +1093,7 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
     // halve gamma, drop the L-BFGS memory, recompute the half step; every group then evaluates psi(u_half)
     auto lip_halve = [&]() {
         lb_active = 0;
-        flags = (flags | F_LBFIRST) & ~F_FBE;
+        flags = (flags | F_LBFIRST) & ~(F_FBE | F_POSTED);
         sput(H_LIP, sget(H_LIP) * 2.0);
         set_gamma(sget(H_GAMMA) / 2.0);
         double2 u[S], gr[S], gs[S], uh[S];
@@ -1141,6 +1245,7 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                 break;
             }
             case PH_STEP_BEGIN: {
+                flags &= ~F_POSTED;
                 double2 u[S], gr[S], uh[S], fpr[S];
                 W.ld(V_U, u);
                 W.ld(V_GRAD, gr);
@@ -1346,6 +1451,14 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                 prof[4] += clock64() - tl0;
                 prof[5]++;
 #endif
+                if (flags & F_MBOX) {  // a helper warp is attached: it evaluates the NG trials after this call's (V_FPR, V_DIR, V_U
+                    const uint32_t mbs = mbox_of((int)(threadIdx.x >> 5));  // are in place: the barrier above)
+                    if (ldsi(mbs + MB_HELPER) != 0) {
+                        const unsigned nseq = (unsigned)ldsi(mbs + MB_SEQ) + 2u;
+                        if (lane == 0) st_release(mbs + MB_SEQ, nseq);
+                        flags |= F_POSTED;
+                    }
+                }
                 // ONE call: group 0 evaluates psi(u_half), groups 1.. the trials tau = 1, 1/2, ...
                 e0 = 0;
                 flags |= F_GFIRST;
@@ -1406,6 +1519,24 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                 st_out.n_grad_evals = iget(I_NGRAD);
                 st_out.reserved = 0;
                 return status;
+            }
+            case PH_HELP: {  // helper mode: wait for the owner's next post (or its retirement), then take the second batch
+                const uint32_t mbm = mbox_of((int)(threadIdx.x >> 5));
+                const uint32_t mbo = mbox_of(ldsi(mbm + MB_HELPER));
+                const unsigned last = (unsigned)ldsi(mbm + MB_DONEQ);
+                unsigned sq;
+                for (;;) {  // every lane polls (warp-uniform)
+                    if (ld_acquire(mbo + MB_STATE) == MB_DONE) return 0;
+                    sq = ld_acquire(mbo + MB_SEQ);
+                    if (sq != last) break;
+                    spin_wait(64);
+                }
+                __syncwarp();
+                stsi(mbm + MB_DONEQ, (int)sq);
+                e0 = NG - 1;  // the owner's call holds psi(u_half) and the trials 0 .. NG-2
+                flags &= ~F_GFIRST;
+                form_trials();
+                break;
             }
             default:
                 break;
@@ -1497,12 +1628,47 @@ __device__ int solve_problem(Warp<G, S>& W, nmpc_stats& st_out, long long* prof_
                     iteration++;
                     step_done();
                 } else {
-                    e0 += NG - gfirst;
-                    flags &= ~F_GFIRST;
-                    form_trials();
-                    phase = PH_LS;
+                    int k = -2;
+                    if ((flags & F_POSTED) && gfirst) {  // the helper warp has evaluated the next NG trials meanwhile
+                        flags &= ~F_POSTED;
+                        k = take_from_helper<G, S>(W.la, W.vstride, W.a_hdr, lane);
+                    }
+                    if (k >= 0) {
+                        e = NG - 1 + k;
+                        iput(I_NGRAD, iget(I_NGRAD) + (e > MAX_LINESEARCH_ITERATIONS ? MAX_LINESEARCH_ITERATIONS : e) + 1);
+                        flags |= F_FBE;
+                        iteration++;
+                        step_done();
+                    } else {
+                        e0 += ((k == -1) ? 2 * NG : NG) - gfirst;
+                        flags &= ~F_GFIRST;
+                        form_trials();
+                        phase = PH_LS;
+                    }
                 }
                 break;
+            }
+            case PH_HELP: {  // helper mode: this warp evaluated the owner's trials NG-1 .. 2NG-2; the results go to its OWN arena
+                double2 gs[S], uh[S];
+                grad_step_half(x, g, gs, uh);
+                double d2 = diff2(gs, uh), gg = dot(g, g);
+                gsum2<G>(d2, gg);
+                const double lhs = psi - (0.5 * sget(H_GAMMA)) * gg + (0.5 * d2) * sget(H_INVG);
+                const int me = (int)(threadIdx.x >> 5);
+                const uint32_t osb = help_u32(2) + (uint32_t)me * help_u32(0);
+                const uint32_t mla = osb + 16u * W.gl + (uint32_t)(4 * grp) * W.vstride;
+#pragma unroll
+                for (int s2 = 0; s2 < S; s2++) {
+                    sts2(mla + 16u * G * s2, x[s2]);
+                    sts2(mla + W.vstride + 16u * G * s2, g[s2]);
+                    sts2(mla + 2u * W.vstride + 16u * G * s2, gs[s2]);
+                    sts2(mla + 3u * W.vstride + 16u * G * s2, uh[s2]);
+                }
+                if (W.gl == 0) sts2(osb + help_u32(1) + 8u * H_HRES + 16u * grp, make_double2(psi, lhs));
+                __syncwarp();
+                const uint32_t mbm = mbox_of(me);
+                if (lane == 0) st_release(mbox_of(ldsi(mbm + MB_HELPER)) + MB_DONEQ, (unsigned)ldsi(mbm + MB_DONEQ));
+                break;  // phase stays PH_HELP
             }
             case PH_RETRY: {  // psi(u_half) after a halving of gamma (every group evaluated the same point)
                 const double cost_half = psi;

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -42,41 +43,120 @@ __device__ __forceinline__ void load_start(const KArgs& a, Warp<G, S>& W, int b,
     __syncwarp();
 }
 
-template <int G, int S>
+#ifndef NMPC_HELP_MAX_WAVES
+#define NMPC_HELP_MAX_WAVES 2
+#endif
+// HELP: the instantiation with helper warps (launch_solve picks it for batches whose tail matters; a batch that keeps every
+// warp busy for most of the launch runs the plain one: its solver loop is a few percent faster without the mailbox code)
+template <int G, int S, bool HELP>
 __global__ void __launch_bounds__(32 * warps_cap(G, S), 1) nmpc_solve_kernel(const __grid_constant__ KArgs a) {
     const nmpc_config& cfg = a.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const Lay L = make_layout(cfg.N_hor, cfg.Nobs, cfg.Ndynobs);
     const int N = cfg.N_hor;
     Warp<G, S> W(cfg, L, warp, lane);
+    if (HELP) {
+    if (lane == 0) {
+        g_help.mb[warp].seq = 0;
+        g_help.mb[warp].done = 0;
+        g_help.mb[warp].state = MB_RUNNING;
+        g_help.mb[warp].helper = 0;
+    }
+    if (threadIdx.x == 0) {
+        g_help.arena_bytes = (unsigned)L.total * 8u;
+        g_help.hdr_off = (unsigned)L.hdr * 8u;
+        g_help.smem_base = (unsigned)__cvta_generic_to_shared(smem);
+    }
+    __syncthreads();
+    }
     // First wave: warp w of CTA c takes problem c + gridDim.x * w, so a batch smaller than the machine is spread
     // over the SMs instead of filling a few CTAs; afterwards the problems come from the atomic queue.
-    bool first = true;
+    // Out of problems: the warp retires and attaches itself as the helper of a warp of this CTA that is still solving and
+    // has none yet — the one that has run the most iterations so far (the long solves are the ones that bound the launch).
+    // It then runs the solver's helper mode through the SAME call site (the kernel holds one copy of the solver).
+    bool first = true, retired = false;
     for (;;) {
         int b = 0;
-        if (first) {
-            b = (int)(blockIdx.x + gridDim.x * warp);
-            first = false;
-        } else {
-            if (lane == 0) b = (int)(gridDim.x * nwarps + atomicAdd(a.counter, 1u));
-            b = __shfl_sync(FULL, b, 0);
+        if (!retired) {
+            if (first) {
+                b = (int)(blockIdx.x + gridDim.x * warp);
+                first = false;
+            } else {
+                if (lane == 0) b = (int)(gridDim.x * nwarps + atomicAdd(a.counter, 1u));
+                b = __shfl_sync(FULL, b, 0);
+            }
+            if (b < a.B && a.order) b = a.order[b];
+            if (b >= a.B) {  // queue empty
+                retired = true;
+                if (HELP) {
+                    __syncwarp();
+                    if (lane == 0) st_release(mbox_of(warp) + MB_STATE, MB_DONE);
+                }
+            } else if (a.skip && a.skip[b]) {
+                continue;
+            }
         }
-        if (b < a.B && a.order) b = a.order[b];
-        if (b >= a.B) break;  // queue empty
-        if (a.skip && a.skip[b]) continue;
-        W.stage(a.P + (size_t)b * a.np);
-        {
+        if (retired) {
+            if (!HELP) break;
+            // Lane w looks at warp slot w; every step of the search is warp-uniform.  A helper must not take issue slots from
+            // a warp that is still solving: it attaches only once no such warp is left on its own sub-partition (slots
+            // w, w+4, w+8 share one scheduler), and waits — asleep — until then.
+            int ow = -1;
+            unsigned seq0 = 0;
+            for (;;) {
+                const uint32_t mbw = mbox_of(lane < nwarps ? lane : 0);
+                const bool running = lane < nwarps && lane != warp && ld_acquire(mbw + MB_STATE) == MB_RUNNING;
+                const bool cand = running && ld_acquire(mbw + MB_HELPER) == 0u;
+                const unsigned rm = __ballot_sync(FULL, running), cm = __ballot_sync(FULL, cand);
+                if (!cm) break;  // nobody left to help
+                if (rm & (0x11111111u << (warp & 3))) {  // a solving warp shares this warp's scheduler: not yet
+                    __nanosleep(4000);
+                    continue;
+                }
+                int key = -1;
+                if (cand) {
+                    const uint32_t oh = g_help.smem_base + (uint32_t)lane * g_help.arena_bytes + g_help.hdr_off + 8u * H_INTS;
+                    key = ldsi(oh + 4u * I_INNER) + ldsi(oh + 4u * I_NUMIT);
+                    key = key < 0 ? 0 : (key > 0x00ffffff ? 0x00ffffff : key);  // (a warp staging its problem: stale counters)
+                    key = (key << 5) | (31 - lane);
+                }
+                const int best = __reduce_max_sync(FULL, key);
+                const int w = 31 - (best & 31);
+                const uint32_t mbo = mbox_of(w);
+                seq0 = ld_acquire(mbo + MB_SEQ);  // before attaching: the owner posts only once it sees a helper
+                unsigned old = 0;
+                if (lane == 0) old = cas_acq_rel(mbo + MB_HELPER, 0u, (unsigned)warp + 1u);
+                old = __shfl_sync(FULL, old, 0);
+                if (old == 0u) {
+                    ow = w;
+                    break;
+                }
+            }
+            if (ow < 0) break;
+            if (lane == 0) {  // this warp's own mailbox now describes its job: the owner's slot and the last seq taken
+                g_help.mb[warp].helper = (unsigned)ow;
+                g_help.mb[warp].done = seq0;
+            }
+            __syncwarp();
+            W.rebase(ow);
+        } else {
+            W.stage(a.P + (size_t)b * a.np);
             double2 u0[S];
             load_start<G, S>(a, W, b, u0);
         }
         nmpc_stats st;
         st.cost = 0.0;
+        const int help = !HELP ? HELP_NONE : (retired ? HELP_HELPER : HELP_OWNER);
 #ifdef NMPC_PROFILE
-        const int status = solve_problem<G, S>(W, st, a.dbg ? a.dbg + (size_t)b * 48 : nullptr);
+        const int status = solve_problem<G, S>(W, st, (a.dbg && !retired) ? a.dbg + (size_t)b * 48 : nullptr, help);
 #else
-        const int status = solve_problem<G, S>(W, st);
+        const int status = solve_problem<G, S>(W, st, nullptr, help);
 #endif
         __syncwarp();
+        if (retired) {  // the owner has retired: look for another one
+            W.rebase(warp);
+            continue;
+        }
         if (W.grp == 0) {
             double2 u[S], yl[S];
             W.ld(V_U, u);
@@ -221,6 +301,7 @@ struct launch_ctx {
 struct nmpc_handle {
     nmpc_config cfg;
     int device, sm_count, np, G, S, warps_per_cta;
+    int help_max_waves;  // batches of up to this many waves of warp slots run the kernel with helper warps (0: never)
     size_t smem_bytes;
     cudaStream_t stream;
     launch_ctx ctx[NMPC_LAUNCH_CTXS];
@@ -301,7 +382,13 @@ const char* nmpc_last_error(nmpc_handle* h) { return h ? h->err : "null handle";
     ((G) == 8 ? ((S) == 2 ? (const void*)KERNEL<8, 2> : (const void*)KERNEL<8, 3>)  \
               : ((S) == 2 ? (const void*)KERNEL<16, 2>                               \
                           : ((S) == 3 ? (const void*)KERNEL<16, 3> : ((S) == 4 ? (const void*)KERNEL<16, 4> : (const void*)KERNEL<16, 6>))))
-static const void* solve_kernel_for(const nmpc_handle* h) { return NMPC_FOR_LAYOUT(nmpc_solve_kernel, h->G, h->S); }
+#define NMPC_FOR_LAYOUT_H(KERNEL, G, S, H)                                        \
+    ((G) == 8 ? ((S) == 2 ? (const void*)KERNEL<8, 2, H> : (const void*)KERNEL<8, 3, H>)  \
+              : ((S) == 2 ? (const void*)KERNEL<16, 2, H>                                  \
+                          : ((S) == 3 ? (const void*)KERNEL<16, 3, H> : ((S) == 4 ? (const void*)KERNEL<16, 4, H> : (const void*)KERNEL<16, 6, H>))))
+static const void* solve_kernel_for(const nmpc_handle* h, bool help) {
+    return help ? NMPC_FOR_LAYOUT_H(nmpc_solve_kernel, h->G, h->S, true) : NMPC_FOR_LAYOUT_H(nmpc_solve_kernel, h->G, h->S, false);
+}
 static const void* probe_kernel_for(const nmpc_handle* h) { return NMPC_FOR_LAYOUT(nmpc_probe_kernel, h->G, h->S); }
 static const void* eval_kernel_for(const nmpc_handle* h) { return NMPC_FOR_LAYOUT(nmpc_eval_kernel, h->G, h->S); }
 
@@ -334,7 +421,7 @@ int nmpc_create(const nmpc_config* cfg, int device, nmpc_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     const Lay L = make_layout(cfg->N_hor, cfg->Nobs, cfg->Ndynobs);
     const size_t per_warp = (size_t)L.total * sizeof(double);
-    const size_t max_smem = prop.sharedMemPerBlockOptin - 64;  // the kernels keep a few static words as well
+    const size_t max_smem = prop.sharedMemPerBlockOptin - 1024;  // the kernels keep some static shared memory as well (mailboxes)
     int w = (int)(max_smem / per_warp);
     if (w < 1) {
         delete h;
@@ -342,8 +429,12 @@ int nmpc_create(const nmpc_config* cfg, int device, nmpc_handle** out) {
     }
     if (w > warps_cap(h->G, h->S)) w = warps_cap(h->G, h->S);
     h->warps_per_cta = w;
+    h->help_max_waves = NMPC_HELP_MAX_WAVES;
+    if (const char* ev = getenv("NMPC_B200_HELP_MAX_WAVES")) h->help_max_waves = atoi(ev);  // tuning / A-B runs
     h->smem_bytes = per_warp * w;
-    e = cudaFuncSetAttribute(solve_kernel_for(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    e = cudaFuncSetAttribute(solve_kernel_for(h, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(solve_kernel_for(h, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(eval_kernel_for(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e == cudaSuccess)
@@ -452,7 +543,11 @@ static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU,
     if (grid > B) grid = B;
     if (grid < 1) grid = 1;
     void* args[] = {&a};
-    CUDA_TRY(h, cudaLaunchKernel(solve_kernel_for(h), dim3(grid), dim3(32 * h->warps_per_cta), args, h->smem_bytes, s));
+    // helper warps pay when a good part of the launch is a tail of long solves on a partly idle machine: small batches
+    // (down to the single problem of nmpc_call) and batches of a few waves; a batch that keeps every warp busy does not
+    const long long slots = (long long)h->sm_count * h->warps_per_cta;
+    const bool help = h->help_max_waves > 0 && (long long)B <= (long long)h->help_max_waves * slots;
+    CUDA_TRY(h, cudaLaunchKernel(solve_kernel_for(h, help), dim3(grid), dim3(32 * h->warps_per_cta), args, h->smem_bytes, s));
     CUDA_TRY(h, cudaEventRecord(c.done, s));
     h->launches++;
     return NMPC_OK;

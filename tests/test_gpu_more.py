@@ -193,3 +193,28 @@ def test_two_rank_nccl_matches_one_gpu(tmp_path, gpu_solver_factory):
     s = gpu_solver_factory(pkg.NmpcConfig.default())
     U, Y, st, _ = s.solve_batch(P)
     assert np.array_equal(got["U"], U) and np.array_equal(got["Y"], Y) and np.array_equal(got["st"], st)
+
+
+@pytest.mark.parametrize("N,Nobs,B", [(20, 10, 1), (20, 10, 5), (20, 10, 150), (20, 10, 1900), (20, 10, 4000), (40, 10, 40), (10, 10, 300)])
+def test_helper_warps_do_not_change_a_bit(monkeypatch, oracle, gpu_solver_factory, N, Nobs, B):
+    """Warps that have run out of problems evaluate the next batch of line-search trials for a warp of their CTA that is
+    still solving (csrc/nmpc_device.cuh: PH_HELP, take_from_helper).  Who evaluates a trial must not matter: the same batch
+    with the helper instantiation of the kernel, without it, and on the oracle — solutions, multipliers, flags and the
+    iteration / evaluation counters all equal, from one problem (eleven idle warps next to the owner) to two waves."""
+    import mpc_trajectory_generator_b200 as pkg
+    cfg = pkg.NmpcConfig.default(N_hor=N, Nobs=Nobs)
+    P = problems.synth(N, Nobs, 3, min(B, 320), seed=40 + B)
+    P = np.ascontiguousarray(np.tile(P, (-(-B // len(P)), 1))[:B])
+    out = {}
+    for waves in ("0", "1000"):
+        monkeypatch.setenv("NMPC_B200_HELP_MAX_WAVES", waves)
+        s = gpu_solver_factory(cfg)
+        out[waves] = s.solve_batch(P)
+    for a, b in zip(out["0"][:3], out["1000"][:3]):
+        assert np.array_equal(a, b, equal_nan=True)
+    for k in ("inner_iterations", "outer_iterations", "n_grad_evals", "n_cost_evals"):
+        assert np.array_equal(out["0"][3][k], out["1000"][3][k]), k
+    n = min(B, 96)
+    ocfg = oracle.default_config(N_hor=N, Nobs=Nobs)
+    U, Y, st, stats = oracle.solve_batch(ocfg, P[:n])
+    assert np.array_equal(st, out["1000"][2][:n]) and np.array_equal(U, out["1000"][0][:n], equal_nan=True)

@@ -114,7 +114,9 @@ def cmd_run(args):
     workload(batch, big)
     for name in names:
         env = dict(os.environ)
-        if name != "base":
+        if name.startswith("waves"):   # the shipped library with another helper-warp threshold (wavesN; waves0 = no helpers)
+            env["NMPC_B200_HELP_MAX_WAVES"] = name[5:]
+        elif name != "base":
             env["NMPC_B200_LIB"] = lib_path(name)
         subprocess.call([sys.executable, os.path.abspath(__file__), "_one", name, str(batch), str(big), str(reps)], env=env)
 
