@@ -90,15 +90,36 @@ def main():
                 kinds = collections.Counter(re.sub(r"\+0x[0-9a-f]+", "", l.split("between ")[1].strip())
                                             for l in txt.splitlines() if "Race reported between" in l)
                 rc = kinds
-    san.append("\nracecheck reports by first access (all are warnings, none is an error):\n")
+    # the same tool with the helper warps switched off (NMPC_B200_HELP_MAX_WAVES=0): the solver itself
+    p0 = os.path.join(G, "r02_san_racecheck_nohelp.log")
+    if os.path.exists(p0):
+        m = re.findall(r"(RACECHECK SUMMARY: .*)", open(p0).read())
+        san.append(f"| racecheck, helper warps off (`NMPC_B200_HELP_MAX_WAVES=0`) | {m[-1] if m else 'no summary line'} |")
+    san.append("\nracecheck reports by first access:\n")
     san += [f"* {n} x `{k}`" for k, n in rc.most_common()]
-    san.append("\nEvery remaining report is on a scalar slot of the arena header (`sget` / `sput` / `iget` / `iput` in "
-               "`csrc/nmpc_device.cuh`: the warp-uniform solver state).  All 32 lanes of the owning warp execute the same store "
-               "with the same value and every lane later reads the value back; racecheck sees lane A's store and lane B's load of "
-               "one address without a barrier in between.  By construction the value a lane reads is the one it stored itself "
-               "(program order) or an identical one.  The cross-group vector exchanges (`Warp::st` / `Warp::ld`) are separated "
-               "by `__syncwarp()` and produce no report; the owner/helper hand-off that round 1's racecheck flagged no longer "
-               "exists.")
+    san.append("""
+**Warnings** (as before the helper warps existed): scalar slots of the arena header (`sget` / `sput` / `iget` / `iput` in
+`csrc/nmpc_device.cuh`: the warp-uniform solver state).  All 32 lanes of the owning warp execute the same store with the
+same value and every lane later reads the value back; racecheck sees lane A's store and lane B's load of one address
+without a barrier in between.  By construction the value a lane reads is the one it stored itself (program order) or an
+identical one.  The cross-group vector exchanges inside a warp (`Warp::st` / `Warp::ld`) are separated by `__syncwarp()`
+and produce no report.
+
+**Errors**: every one is an access pair between an owner warp and its helper warp (DESIGN.md section 5, "Helper warps") —
+with the helper warps off the same workload reports none.  The two warps synchronise through the mailbox words with
+`st.release.cta` / `ld.acquire.cta` (and `__syncwarp()` inside each warp before the release and after the acquire);
+racecheck only models barriers, so it reports every pair of accesses the flags order:
+
+| first access | second access | what it is | what orders it |
+|---|---|---|---|
+| read `lds2` (helper: `form_trials` loads the owner's V_U, V_FPR, V_DIR) | write `sts2_if` (owner: `Warp::st` of those vectors in PH_STEP_BEGIN / at an accepted trial) | the helper reads the trial inputs of post s | the owner stores them, `__syncwarp()`, then `st.release` of `seq = s`; the helper's `ld.acquire` of `seq` precedes its loads.  The owner overwrites V_U only after it has either taken the helper's results for s or accepted a trial of its own call — in the second case a late helper may read a half-written V_U, and its results for s are never taken (`done == seq` is only waited for when the owner's call accepted nothing) |
+| write `sts2` / `sts1` (helper: PH_HELP stores x, grad, gradient step, half step per trial and (psi, lhs) into its OWN arena) | read `lds2` / `lds1` (owner: `take_from_helper`) | the owner takes the results of post s | helper: stores, `__syncwarp()`, `st.release` of `done = s`; owner: `ld.acquire` until `done == s`, then reads.  The helper overwrites its arena only after it has seen `seq != s`, which the owner writes after it has finished copying |
+| write `st_release` | read `ld_acquire` / `ldsi` | the mailbox words themselves (`seq`, `done`, `state`, `helper`) | these ARE the synchronisation |
+| read `ldsi` | write `stsi` / atomic | a retiring warp reads the iteration counters of the solving warps of its CTA to choose the one it helps (any value is acceptable: a heuristic), and the owner reads its `helper` word, which the helper sets once with a compare-and-swap | nothing needs to |
+| read `lds1` (helper: the owner's step size, penalty and problem data inside the evaluation) | write `sts1` (owner: `sput`) | the helper evaluates with the owner's header | those slots change only in `lip_halve` and at the end of an inner solve, and the helper's results of a post are not taken after either |
+
+memcheck, synccheck (every `__syncwarp` / `__shfl_sync` / vote with the full mask, also in helper mode) and initcheck are clean
+with the helper warps on.""")
     with open(os.path.join(P, "r02_sanitizers.md"), "w") as f:
         f.write("\n".join(san) + "\n")
     print("profiles written")
