@@ -486,6 +486,38 @@ def main():
         fleet.close()
         fsolver.close()
 
+    # single calls (the reference's own use: one robot, one solve per control period — BASELINE.md §3 (i)): problems of the
+    # headline batch one at a time through the C ABI from host memory (cold start, helper warps next to the owner warp),
+    # and the same problems on ONE host thread of the CPU restatement
+    if args.extra != "off" and rank == 0:
+        from oracle import oracle_c as _oc
+        _oc.build()
+        _oc.use_native()
+        ocfg = _oc.default_config(N_hor=N, Nobs=Nobs, Ndynobs=Nd, ang_vel_max=hc.ang_vel_max, ang_acc_max=hc.ang_acc_max)
+        pick = np.arange(0, B, max(1, B // 96))[:96]
+        g_wall, g_kern, c_wall, its = [], [], [], []
+        for i in pick:
+            Pi = np.ascontiguousarray(P[i:i + 1])
+            t0 = time.perf_counter()
+            _, _, _, sti = solver.solve_batch(Pi)
+            g_wall.append(1e3 * (time.perf_counter() - t0))
+            g_kern.append(float(solver.last_kernel_ms))
+            its.append(int(sti["inner_iterations"][0]))
+            t0 = time.perf_counter()
+            _oc.solve_batch(ocfg, Pi, nthreads=1)
+            c_wall.append(1e3 * (time.perf_counter() - t0))
+
+        def dist(v):
+            v = np.asarray(v)
+            return {"median": float(np.median(v)), "p90": float(np.percentile(v, 90)), "p99": float(np.percentile(v, 99)),
+                    "mean": float(v.mean()), "max": float(v.max())}
+        extra.append({"config": "single_call", "workload": f"{len(pick)} problems of the headline batch, one per call, cold start",
+                      "unit": "ms per solve", "gpu_call_wall_ms": dist(g_wall), "gpu_kernel_ms": dist(g_kern),
+                      "cpu_single_thread_ms": dist(c_wall), "inner_iterations": dist(its),
+                      "api": "NmpcSolver.solve_batch -> nmpc_solve_batch (C ABI), B = 1, pageable host buffers",
+                      "value": float(np.mean(g_wall)), "ms_per_step": float(np.mean(g_wall)), "batch_per_gpu": 1, "steps": len(pick),
+                      "exit_status_counts": [], "inner_iterations_mean": float(np.mean(its)), "workload_generation_s": 0.0})
+
     if rank == 0:
         peak, peak_src = load_peaks()
         abytes = algorithmic_bytes(N, Nobs, Nd)
