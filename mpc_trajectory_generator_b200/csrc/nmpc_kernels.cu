@@ -43,6 +43,9 @@ __device__ __forceinline__ void load_start(const KArgs& a, Warp<G, S>& W, int b,
     __syncwarp();
 }
 
+#ifndef NMPC_HELP_SHARE
+#define NMPC_HELP_SHARE 0  // solving warps a helper tolerates on its own scheduler (1: measured neutral to worse)
+#endif
 #ifndef NMPC_HELP_MAX_WAVES
 #define NMPC_HELP_MAX_WAVES 2
 #endif
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(32 * warps_cap(G, S), 1) nmpc_solve_kernel(con
                 const bool cand = running && ld_acquire(mbw + MB_HELPER) == 0u;
                 const unsigned rm = __ballot_sync(FULL, running), cm = __ballot_sync(FULL, cand);
                 if (!cm) break;  // nobody left to help
-                if (rm & (0x11111111u << (warp & 3))) {  // a solving warp shares this warp's scheduler: not yet
+                if (__popc(rm & (0x11111111u << (warp & 3))) > NMPC_HELP_SHARE) {  // a solving warp shares this warp's scheduler: not yet
                     __nanosleep(4000);
                     continue;
                 }
@@ -490,6 +493,10 @@ int nmpc_ping(nmpc_handle* h) {
     return NMPC_OK;
 }
 
+#ifdef NMPC_DEBUG_ORDER
+static const int32_t* g_dbg_order = nullptr;
+static int32_t g_dbg_order_n = 0;
+#endif
 static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU, double* dY, int32_t* dstatus,
                         nmpc_stats* dstats, cudaStream_t s, const int32_t* dskip = nullptr, const int32_t* dorder = nullptr) {
     KArgs a;
@@ -510,6 +517,9 @@ static int launch_solve(nmpc_handle* h, int32_t B, const double* dP, double* dU,
     if (c.used) CUDA_TRY(h, cudaStreamWaitEvent(s, c.done, 0));
     c.used = true;
     a.counter = c.counter;
+#ifdef NMPC_DEBUG_ORDER
+    if (!dorder && g_dbg_order && g_dbg_order_n == B) dorder = g_dbg_order, a.order = dorder;
+#endif
     if (NMPC_AUTO_ORDER && !dorder && B > h->sm_count * h->warps_per_cta) {
         // more problems than warp slots: rank them with one gradient evaluation each and start the long ones first
         if (B > c.pcap) {
@@ -1013,6 +1023,10 @@ int nmpc_fleet_log(nmpc_fleet* f, double* log, int32_t* n_logged) {
 
 #ifdef NMPC_PROFILE
 void nmpc_debug_set_buffer(void* p) { g_dbg = (long long*)p; }
+#endif
+#ifdef NMPC_DEBUG_ORDER
+// experiments only (tools/variants.py builds): hand-out order for the next launches of any handle (device pointer, B entries)
+void nmpc_debug_set_order(const int32_t* dorder, int32_t n) { g_dbg_order = dorder; g_dbg_order_n = n; }
 #endif
 
 int64_t nmpc_launch_count(nmpc_handle* h) { return h ? h->launches : 0; }
