@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 LIB = "mpc_trajectory_generator_b200/libnmpc_b200.so"
-KERNEL = sys.argv[1] if len(sys.argv) > 1 else "_Z17nmpc_solve_kernelILi8ELi3EEv5KArgs"   # N = 20: G = 8, S = 3
+KERNEL = sys.argv[1] if len(sys.argv) > 1 else "_Z17nmpc_solve_kernelILi8ELi3ELb0EEv5KArgs"   # N = 20: G = 8, S = 3, without helper warps (Lb1: with)
 
 
 def main():
