@@ -16,13 +16,13 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 REL_TOL = 1e-4
 
 
-def _compare(U, st, Us, sts, min_converged):
+def _compare(U, st, Us, sts, min_converged, max_flag_mismatch=0.02):
     both = (st == 0) & (sts == 0)
     rel = np.linalg.norm(U - Us, axis=1) / np.maximum(np.linalg.norm(Us, axis=1), 1e-12)
     assert both.sum() >= min_converged
     assert rel[both].max() <= REL_TOL, f"converged problems differ by {rel[both].max():.2e}"
     flag_mismatch = float((st != sts).mean())
-    assert flag_mismatch <= 0.02, f"{flag_mismatch:.3%} of the exit flags differ"
+    assert flag_mismatch <= max_flag_mismatch, f"{flag_mismatch:.3%} of the exit flags differ"
     assert not np.any((st == 3) | (sts == 3))
     rest = ~both
     return {"converged_both": int(both.sum()), "max_rel_converged": float(rel[both].max()),
@@ -90,3 +90,23 @@ def test_gpu_vs_serial_arithmetic(oracle, gpu_solver_factory):
     U, Y, st, _ = s.solve_batch(P)
     Us, Ys, sts, _ = oracle.solve_batch(cfg, P, serial=True)
     print("config 2:", _compare(U, st, Us, sts, min_converged=256))
+
+
+def test_contract_oracle_vs_serial_arithmetic_config4_setup(oracle):
+    """BASELINE config 4's setup at test size (map 11, N=40 — two 16-lane groups of three steps: another reduction
+    layout than N=20 — smooth_velocity.yaml weights and bounds, warm-started receding-horizon steps recorded in closed
+    loop): the same bar against the serial-arithmetic build."""
+    from mpc_trajectory_generator_b200 import workloads
+    from mpc_trajectory_generator_b200.host import assembly
+    hc = assembly.HostConfig.smooth_velocity(N_hor=40)
+    kw = dict(N_hor=hc.N_hor, Nobs=hc.Nobs, Ndynobs=hc.Ndynobs, ang_vel_max=hc.ang_vel_max, ang_acc_max=hc.ang_acc_max,
+              lin_vel_min=hc.lin_vel_min, lin_vel_max=hc.lin_vel_max, lin_acc_min=hc.lin_acc_min, lin_acc_max=hc.lin_acc_max,
+              ts=hc.ts)
+    cfg = oracle.default_config(**kw)
+    rec = workloads.closed_loop_batch(hc, lambda P, U0, Y0: oracle.solve_batch(cfg, P, U0, Y0)[:3], complexity=11,
+                                      robots=10, steps=40, seed=4, sincos=oracle.sincos)
+    Us, Ys, sts, _ = oracle.solve_batch(cfg, rec["P"], rec["U0"], rec["Y0"], serial=True)
+    # (most of these solves run into the iteration budget — BASELINE config 4 is like that — so fewer converge on both
+    #  sides and a borderline flag weighs more than in the N=20 sets)
+    r = _compare(rec["U"], rec["status"], Us, sts, min_converged=30, max_flag_mismatch=0.04)
+    print("config 4 setup:", r)
